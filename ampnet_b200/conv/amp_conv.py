@@ -1,0 +1,76 @@
+"""Drop-in mirror of the reference's ``AMPConv`` (``src/ampnet/conv/amp_conv.py:9-51``).
+
+Same constructor ``AMPConv(embed_dim, num_heads)``, same ``forward(x, edge_index)`` returning
+``[N, F * embed_dim]``, same parameter names (state_dict keys
+``multi_head_attention.{in_proj_weight,in_proj_bias,out_proj.weight,out_proj.bias}``, so
+checkpoints move both ways), same public attributes ``num_heads``, ``embed_dim``,
+``attn_output`` ([E, F, d], after out_proj) and ``attn_output_weights`` ([E, F, F], averaged over
+heads, original edge order).  Underneath, the eager PyG + ``nn.MultiheadAttention`` chain is
+replaced by the CUDA kernels behind ``include/ampconv.h``; there is no CPU fallback.
+
+Differences that are deliberate supersets of the reference's behaviour:
+* a width that is not a multiple of ``embed_dim`` raises ``ValueError`` (the reference prints
+  "Error, invalid configuration" and then fails inside ``reshape``; ``amp_conv.py:32-36``);
+* the two side outputs are computed lazily on first read instead of on every forward (at the
+  ogbn-arxiv shape ``attn_output_weights`` alone would be 76 GB).
+"""
+import torch
+import torch.nn as nn
+
+from .. import functional as F_
+from ..graph import get_graph
+
+
+class AMPConv(nn.Module):
+    def __init__(self, embed_dim, num_heads, mode="fp32"):
+        super().__init__()
+        self._holder = {}
+        self._attn_output_weights = None
+        self._attn_output = None
+        self.num_heads = num_heads
+        self.embed_dim = embed_dim
+        self.mode = mode
+        # Parameter container only (identical names, shapes and initialisation to the reference's
+        # nn.MultiheadAttention(embed_dim, num_heads, batch_first=True, bias=True), amp_conv.py:18-22);
+        # its forward is never called.
+        self.multi_head_attention = nn.MultiheadAttention(
+            embed_dim=embed_dim, num_heads=num_heads, batch_first=True, bias=True)
+
+    def forward(self, x, edge_index):
+        F_.check_inputs(x, edge_index, self.embed_dim, self.num_heads)
+        mha = self.multi_head_attention
+        graph = get_graph(edge_index, x.shape[0])
+        self._attn_output_weights = None
+        self._attn_output = None
+        self._holder = {}
+        return F_.amp_conv(x, graph, mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight,
+                           mha.out_proj.bias, self.num_heads, mode=self.mode, holder=self._holder)
+
+    # --- side outputs of the reference (amp_conv.py:12-13,39), materialised on first read -------------
+    @property
+    def attn_output_weights(self):
+        if self._attn_output_weights is None and "saved" in self._holder:
+            self._attn_output_weights = F_.attention_weights(self._holder["saved"])
+        return self._attn_output_weights
+
+    @attn_output_weights.setter
+    def attn_output_weights(self, value):
+        self._attn_output_weights = value
+
+    @property
+    def attn_output(self):
+        if self._attn_output is None and "saved" in self._holder:
+            w_out, b_out = self._holder["params"]
+            self._attn_output = F_.edge_output(self._holder["saved"], w_out, b_out)
+        return self._attn_output
+
+    @attn_output.setter
+    def attn_output(self, value):
+        self._attn_output = value
+
+    def extra_repr(self):
+        return f"embed_dim={self.embed_dim}, num_heads={self.num_heads}, mode={self.mode!r}"
+
+
+class AMPConvV2(AMPConv):
+    """The reference's ``AMPConvV2`` (``amp_conv.py:54-89``) is behaviourally identical to ``AMPConv``."""

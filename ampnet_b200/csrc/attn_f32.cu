@@ -1,0 +1,527 @@
+// Strict fp32 fused attention + mean aggregation for AMPConv (CUDA cores; any F, d, H with hd <= 128).
+//
+// Replaces, per layer, the reference's per-edge chain (src/ampnet/conv/amp_conv.py:24-51 ->
+// torch.nn.MultiheadAttention; era arithmetic src/ampnet/conv/custom_multihead_attn_forward.py
+// :4140-4186 scaled-dot-product, :4376-4387 head split, :4441-4442 head-mean of the weights)
+// and PyG's scatter-mean (amp_conv.py:11) with destination-sorted kernels that never materialise
+// the [E,F,d] messages or the [E,H,F,F] probabilities.
+//
+// Thread mapping: one thread owns one (token, head) row of one node; rows are ordered head-major
+// (row = h*F + token) so a warp reads one head's K/V slice from shared memory as a broadcast.
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "gemm_f32.cuh"
+
+namespace ampconv {
+namespace {
+
+template <int HD>
+struct Head {
+  static constexpr int MAX = HD > 0 ? HD : 128;
+  static constexpr bool VEC = (HD > 0) && (HD % 4 == 0);
+  __device__ static __forceinline__ int dim(int hd_rt) { return HD > 0 ? HD : hd_rt; }
+};
+
+struct RowBlock {
+  int r, h, i, h_lo, n_heads, c0, ncols;
+  bool active;
+};
+
+__device__ __forceinline__ RowBlock row_block(int F, int H, int hd) {
+  RowBlock b;
+  const int R = F * H;
+  const int r0 = blockIdx.y * blockDim.x;
+  b.r = r0 + threadIdx.x;
+  b.active = b.r < R;
+  const int rr = b.active ? b.r : r0;
+  b.h = rr / F;
+  b.i = rr - b.h * F;
+  const int r_last = min(R, r0 + (int)blockDim.x) - 1;
+  b.h_lo = r0 / F;
+  b.n_heads = r_last / F - b.h_lo + 1;
+  b.c0 = b.h_lo * hd;
+  b.ncols = b.n_heads * hd;
+  return b;
+}
+
+// Cooperative copy of `rows` x `ncols` floats (global row stride ld) into a dense smem tile.
+template <bool VEC>
+__device__ __forceinline__ void load_tile(float* __restrict__ dst, const float* __restrict__ src,
+                                          int64_t ld, int rows, int ncols) {
+  if (VEC) {
+    const int nv = ncols >> 2;
+    for (int idx = threadIdx.x; idx < rows * nv; idx += blockDim.x) {
+      int rr = idx / nv, cv = idx - rr * nv;
+      reinterpret_cast<float4*>(dst)[idx] = *reinterpret_cast<const float4*>(src + rr * ld + 4 * cv);
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < rows * ncols; idx += blockDim.x) {
+      int rr = idx / ncols, c = idx - rr * ncols;
+      dst[idx] = src[rr * ld + c];
+    }
+  }
+}
+
+template <int HD>
+__device__ __forceinline__ float dot_row(const float* __restrict__ a_reg, const float* __restrict__ b_smem, int hd) {
+  float s = 0.f;
+  if (Head<HD>::VEC) {
+#pragma unroll
+    for (int c = 0; c < Head<HD>::MAX; c += 4) {
+      float4 b = *reinterpret_cast<const float4*>(b_smem + c);
+      s = fmaf(a_reg[c], b.x, s);
+      s = fmaf(a_reg[c + 1], b.y, s);
+      s = fmaf(a_reg[c + 2], b.z, s);
+      s = fmaf(a_reg[c + 3], b.w, s);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < Head<HD>::MAX; ++c)
+      if (c < hd) s = fmaf(a_reg[c], b_smem[c], s);
+  }
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------
+// Forward.  PER_EDGE = false: agg[n] = inv_deg[n] * sum_e softmax(q k^T) v, lse saved.
+//           PER_EDGE = true : edge_out[dst_eid[p]] = softmax(q k^T) v (attn_output side output,
+//                             before out_proj), nothing aggregated.
+// ------------------------------------------------------------------------------------------
+template <int HD, bool PER_EDGE>
+__global__ void __launch_bounds__(256)
+attn_fwd_f32_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ rowptr,
+                    const int32_t* __restrict__ dst_src, const int32_t* __restrict__ dst_eid,
+                    const float* __restrict__ inv_deg, float* __restrict__ out, float* __restrict__ lse,
+                    int F, int d, int H, int hd_rt, int TJ, float scale) {
+  constexpr int HM = Head<HD>::MAX;
+  const int hd = Head<HD>::dim(hd_rt);
+  extern __shared__ __align__(16) float smem[];
+  const RowBlock b = row_block(F, H, hd);
+  float* Ks = smem;
+  float* Vs = smem + (size_t)TJ * b.ncols;
+  const int64_t n = blockIdx.x;
+  const int64_t ld = 3 * (int64_t)d;
+
+  float q[HM], acc[HM], total[HM];
+#pragma unroll
+  for (int c = 0; c < HM; ++c) {
+    q[c] = (b.active && c < hd) ? qkv[(n * F + b.i) * ld + b.h * hd + c] * scale : 0.f;
+    total[c] = 0.f;
+  }
+  const int hoff = (b.h - b.h_lo) * hd;
+  const int p_begin = rowptr[n], p_end = rowptr[n + 1];
+  for (int p = p_begin; p < p_end; ++p) {
+    const int64_t s = dst_src[p];
+    float m = -CUDART_INF_F, l = 0.f;
+#pragma unroll
+    for (int c = 0; c < HM; ++c) acc[c] = 0.f;
+    for (int j0 = 0; j0 < F; j0 += TJ) {
+      const int tj = min(TJ, F - j0);
+      __syncthreads();
+      const float* base = qkv + (s * F + j0) * ld + b.c0;
+      load_tile<Head<HD>::VEC>(Ks, base + d, ld, tj, b.ncols);
+      load_tile<Head<HD>::VEC>(Vs, base + 2 * d, ld, tj, b.ncols);
+      __syncthreads();
+      if (b.active) {
+        for (int jj = 0; jj < tj; jj += 4) {
+          float sc[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            sc[u] = (jj + u < tj) ? dot_row<HD>(q, Ks + (size_t)(jj + u) * b.ncols + hoff, hd) : -CUDART_INF_F;
+          const float m_new = fmaxf(m, fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3])));
+          const float corr = __expf(m - m_new);
+          l *= corr;
+#pragma unroll
+          for (int c = 0; c < HM; ++c) acc[c] *= corr;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (jj + u < tj) {
+              const float pj = __expf(sc[u] - m_new);
+              l += pj;
+              const float* vr = Vs + (size_t)(jj + u) * b.ncols + hoff;
+#pragma unroll
+              for (int c = 0; c < HM; ++c)
+                if (c < hd) acc[c] = fmaf(pj, vr[c], acc[c]);
+            }
+          }
+          m = m_new;
+        }
+      }
+    }
+    if (b.active) {
+      const float inv_l = 1.f / l;
+      if (PER_EDGE) {
+        float* o = out + ((int64_t)dst_eid[p] * F + b.i) * d + b.h * hd;
+#pragma unroll
+        for (int c = 0; c < HM; ++c)
+          if (c < hd) o[c] = acc[c] * inv_l;
+      } else {
+#pragma unroll
+        for (int c = 0; c < HM; ++c) total[c] = fmaf(acc[c], inv_l, total[c]);
+        lse[((int64_t)p * H + b.h) * F + b.i] = m + __logf(l);
+      }
+    }
+  }
+  if (!PER_EDGE && b.active) {
+    const float w = inv_deg[n];
+    float* o = out + (n * F + b.i) * d + b.h * hd;
+#pragma unroll
+    for (int c = 0; c < HM; ++c)
+      if (c < hd) o[c] = total[c] * w;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Backward pass A (destination-sorted, row owner = (dst token i, head)):
+//   delta[p,h,i] = sum_j P_ij dP_ij ,  d_q[i] = scale * sum_e (sum_j P dP k_j - delta * sum_j P k_j)
+// with P = exp(scale q k - lse), dP_ij = dO_i . v_j and dO = d_agg (already divided by in-degree).
+// ------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(256)
+attn_bwd_dq_f32_kernel(const float* __restrict__ qkv, const float* __restrict__ d_agg,
+                       const float* __restrict__ lse, const int32_t* __restrict__ rowptr,
+                       const int32_t* __restrict__ dst_src, float* __restrict__ d_qkv,
+                       float* __restrict__ delta, int F, int d, int H, int hd_rt, int TJ, float scale) {
+  constexpr int HM = Head<HD>::MAX;
+  const int hd = Head<HD>::dim(hd_rt);
+  extern __shared__ __align__(16) float smem[];
+  const RowBlock b = row_block(F, H, hd);
+  float* Ks = smem;
+  float* Vs = smem + (size_t)TJ * b.ncols;
+  const int64_t n = blockIdx.x;
+  const int64_t ld = 3 * (int64_t)d;
+
+  float q[HM], go[HM], dq[HM], A[HM], B[HM];
+#pragma unroll
+  for (int c = 0; c < HM; ++c) {
+    const bool ok = b.active && c < hd;
+    q[c] = ok ? qkv[(n * F + b.i) * ld + b.h * hd + c] * scale : 0.f;
+    go[c] = ok ? d_agg[(n * F + b.i) * d + b.h * hd + c] : 0.f;
+    dq[c] = 0.f;
+  }
+  const int hoff = (b.h - b.h_lo) * hd;
+  const int p_begin = rowptr[n], p_end = rowptr[n + 1];
+  for (int p = p_begin; p < p_end; ++p) {
+    const int64_t s = dst_src[p];
+    const int64_t stat = ((int64_t)p * H + b.h) * F + b.i;
+    const float L = b.active ? lse[stat] : 0.f;
+    float dl = 0.f;
+#pragma unroll
+    for (int c = 0; c < HM; ++c) { A[c] = 0.f; B[c] = 0.f; }
+    for (int j0 = 0; j0 < F; j0 += TJ) {
+      const int tj = min(TJ, F - j0);
+      __syncthreads();
+      const float* base = qkv + (s * F + j0) * ld + b.c0;
+      load_tile<Head<HD>::VEC>(Ks, base + d, ld, tj, b.ncols);
+      load_tile<Head<HD>::VEC>(Vs, base + 2 * d, ld, tj, b.ncols);
+      __syncthreads();
+      if (b.active) {
+        for (int jj = 0; jj < tj; ++jj) {
+          const float* kr = Ks + (size_t)jj * b.ncols + hoff;
+          const float* vr = Vs + (size_t)jj * b.ncols + hoff;
+          const float pj = __expf(dot_row<HD>(q, kr, hd) - L);
+          const float w = pj * dot_row<HD>(go, vr, hd);
+          dl += w;
+#pragma unroll
+          for (int c = 0; c < HM; ++c)
+            if (c < hd) { A[c] = fmaf(w, kr[c], A[c]); B[c] = fmaf(pj, kr[c], B[c]); }
+        }
+      }
+    }
+    if (b.active) {
+      delta[stat] = dl;
+#pragma unroll
+      for (int c = 0; c < HM; ++c) dq[c] += scale * (A[c] - dl * B[c]);
+    }
+  }
+  if (b.active) {
+    float* o = d_qkv + (n * F + b.i) * ld + b.h * hd;
+#pragma unroll
+    for (int c = 0; c < HM; ++c)
+      if (c < hd) o[c] = dq[c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Backward pass B (source-sorted, column owner = (src token j, head)):
+//   d_v[j] = sum_e sum_i P_ij dO_i ,  d_k[j] = scale * sum_e sum_i P_ij (dP_ij - delta_i) q_i
+// accumulated over the out-edges of the source in registers (no atomics, deterministic).
+// ------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(256)
+attn_bwd_dkv_f32_kernel(const float* __restrict__ qkv, const float* __restrict__ d_agg,
+                        const float* __restrict__ lse, const float* __restrict__ delta,
+                        const int32_t* __restrict__ src_rowptr, const int32_t* __restrict__ src_dst,
+                        const int32_t* __restrict__ src_pos, float* __restrict__ d_qkv,
+                        int F, int d, int H, int hd_rt, int TI, float scale) {
+  constexpr int HM = Head<HD>::MAX;
+  const int hd = Head<HD>::dim(hd_rt);
+  extern __shared__ __align__(16) float smem[];
+  const RowBlock b = row_block(F, H, hd);     // here the "row" is the source token j
+  float* Qs = smem;
+  float* Gs = Qs + (size_t)TI * b.ncols;
+  float* Ls = Gs + (size_t)TI * b.ncols;       // [n_heads][TI]
+  float* Ds = Ls + (size_t)b.n_heads * TI;
+  const int64_t s = blockIdx.x;
+  const int64_t ld = 3 * (int64_t)d;
+
+  float kj[HM], vj[HM], dk[HM], dv[HM];
+#pragma unroll
+  for (int c = 0; c < HM; ++c) {
+    const bool ok = b.active && c < hd;
+    kj[c] = ok ? qkv[(s * F + b.i) * ld + d + b.h * hd + c] * scale : 0.f;
+    vj[c] = ok ? qkv[(s * F + b.i) * ld + 2 * d + b.h * hd + c] : 0.f;
+    dk[c] = 0.f;
+    dv[c] = 0.f;
+  }
+  const int hoff = (b.h - b.h_lo) * hd;
+  const int e_begin = src_rowptr[s], e_end = src_rowptr[s + 1];
+  for (int e2 = e_begin; e2 < e_end; ++e2) {
+    const int64_t t = src_dst[e2];
+    const int64_t p = src_pos[e2];
+    for (int i0 = 0; i0 < F; i0 += TI) {
+      const int ti = min(TI, F - i0);
+      __syncthreads();
+      load_tile<Head<HD>::VEC>(Qs, qkv + (t * F + i0) * ld + b.c0, ld, ti, b.ncols);
+      load_tile<Head<HD>::VEC>(Gs, d_agg + (t * F + i0) * d + b.c0, d, ti, b.ncols);
+      for (int idx = threadIdx.x; idx < b.n_heads * ti; idx += blockDim.x) {
+        const int hh = idx / ti, ii = idx - hh * ti;
+        const int64_t stat = (p * H + b.h_lo + hh) * F + i0 + ii;
+        Ls[hh * TI + ii] = lse[stat];
+        Ds[hh * TI + ii] = delta[stat];
+      }
+      __syncthreads();
+      if (b.active) {
+        const float* Lh = Ls + (b.h - b.h_lo) * TI;
+        const float* Dh = Ds + (b.h - b.h_lo) * TI;
+        for (int ii = 0; ii < ti; ++ii) {
+          const float* qr = Qs + (size_t)ii * b.ncols + hoff;
+          const float* gr = Gs + (size_t)ii * b.ncols + hoff;
+          const float pj = __expf(dot_row<HD>(kj, qr, hd) - Lh[ii]);   // kj carries the scale
+          const float ds = pj * (dot_row<HD>(vj, gr, hd) - Dh[ii]) * scale;
+#pragma unroll
+          for (int c = 0; c < HM; ++c)
+            if (c < hd) { dv[c] = fmaf(pj, gr[c], dv[c]); dk[c] = fmaf(ds, qr[c], dk[c]); }
+        }
+      }
+    }
+  }
+  if (b.active) {
+    float* ok_ = d_qkv + (s * F + b.i) * ld + d + b.h * hd;
+    float* ov_ = d_qkv + (s * F + b.i) * ld + 2 * d + b.h * hd;
+#pragma unroll
+    for (int c = 0; c < HM; ++c)
+      if (c < hd) { ok_[c] = dk[c]; ov_[c] = dv[c]; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Head-averaged attention coefficients in original edge order (opt-in side output).
+// grid = (edge slot, 16x16 tiles of the F x F matrix), block = 16 x 16.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+attn_weights_f32_kernel(const float* __restrict__ qkv, const float* __restrict__ lse,
+                        const int32_t* __restrict__ slot_dst, const int32_t* __restrict__ dst_src,
+                        const int32_t* __restrict__ dst_eid, float* __restrict__ weights,
+                        int F, int d, int H, float scale) {
+  extern __shared__ __align__(16) float smem[];
+  const int hd = d / H;
+  float* Qs = smem;                       // [16][hd+1]
+  float* Ks = smem + 16 * (hd + 1);       // [16][hd+1]
+  const int64_t p = blockIdx.x;
+  const int tiles = (F + 15) / 16;
+  const int i0 = (blockIdx.y / tiles) * 16, j0 = (blockIdx.y % tiles) * 16;
+  const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
+  const int64_t t = slot_dst[p], s = dst_src[p];
+  const int64_t ld = 3 * (int64_t)d;
+  float w = 0.f;
+  for (int h = 0; h < H; ++h) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 16 * hd; idx += 256) {
+      int rr = idx / hd, c = idx - rr * hd;
+      Qs[rr * (hd + 1) + c] = (i0 + rr < F) ? qkv[(t * F + i0 + rr) * ld + h * hd + c] : 0.f;
+      Ks[rr * (hd + 1) + c] = (j0 + rr < F) ? qkv[(s * F + j0 + rr) * ld + d + h * hd + c] : 0.f;
+    }
+    __syncthreads();
+    if (i0 + ti < F && j0 + tj < F) {
+      float sc = 0.f;
+      for (int c = 0; c < hd; ++c) sc = fmaf(Qs[ti * (hd + 1) + c], Ks[tj * (hd + 1) + c], sc);
+      w += __expf(sc * scale - lse[(p * H + h) * F + i0 + ti]);
+    }
+  }
+  if (i0 + ti < F && j0 + tj < F)
+    weights[((int64_t)dst_eid[p] * F + i0 + ti) * F + j0 + tj] = w / (float)H;
+}
+
+// slot -> destination node, recovered from the row pointer (one thread per node).
+__global__ void slot_dst_kernel(const int32_t* __restrict__ rowptr, int64_t N, int32_t* __restrict__ slot_dst) {
+  int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  for (int p = rowptr[n]; p < rowptr[n + 1]; ++p) slot_dst[p] = (int32_t)n;
+}
+
+struct LaunchPlan {
+  int block, row_blocks, tile, ncols_max;
+  size_t smem;
+};
+
+LaunchPlan plan_rows(int F, int H, int hd, int buffers_per_row_tile) {
+  LaunchPlan lp;
+  const int R = F * H;
+  lp.block = R >= 256 ? 256 : ((R + 31) / 32) * 32;
+  lp.row_blocks = (R + lp.block - 1) / lp.block;
+  // heads spanned by one row block (rows are head-major)
+  int span = 1;
+  for (int rb = 0; rb < lp.row_blocks; ++rb) {
+    int r0 = rb * lp.block, r1 = (R < r0 + lp.block ? R : r0 + lp.block) - 1;
+    int sp = r1 / F - r0 / F + 1;
+    if (sp > span) span = sp;
+  }
+  lp.ncols_max = span * hd;
+  int tile = 4096 / lp.ncols_max;
+  if (tile < 1) tile = 1;
+  if (tile > F) tile = F;
+  lp.tile = tile;
+  lp.smem = (size_t)buffers_per_row_tile * tile * lp.ncols_max * sizeof(float);
+  return lp;
+}
+
+bool valid_shape(int64_t N, int64_t E, int F, int d, int H) {
+  return N >= 0 && E >= 0 && F > 0 && d > 0 && H > 0 && d % H == 0;
+}
+
+#define AMPCONV_DISPATCH_HD(hd, CALL)      \
+  switch (hd) {                            \
+    case 1: { CALL(1); } break;            \
+    case 2: { CALL(2); } break;            \
+    case 3: { CALL(3); } break;            \
+    case 4: { CALL(4); } break;            \
+    case 8: { CALL(8); } break;            \
+    case 16: { CALL(16); } break;          \
+    case 32: { CALL(32); } break;          \
+    default: { CALL(0); } break;           \
+  }
+
+}  // namespace
+}  // namespace ampconv
+
+using namespace ampconv;
+
+extern "C" int ampconv_attn_fwd_f32(const float* qkv, const int32_t* dst_rowptr, const int32_t* dst_src,
+                                    const float* inv_deg, float* agg, float* lse,
+                                    int64_t N, int64_t E, int F, int d, int H, void* stream_) {
+  AMPCONV_REQUIRE(valid_shape(N, E, F, d, H));
+  if (N == 0) return AMPCONV_OK;
+  AMPCONV_REQUIRE(qkv && dst_rowptr && inv_deg && agg && (E == 0 || (dst_src && lse)));
+  const int hd = d / H;
+  if (hd > 128) return AMPCONV_ERR_UNSUPPORTED;
+  LaunchPlan lp = plan_rows(F, H, hd, 2);
+  dim3 grid((unsigned)N, (unsigned)lp.row_blocks);
+  const float scale = 1.0f / sqrtf((float)hd);
+  cudaStream_t stream = as_stream(stream_);
+#define CALL(HDV)                                                                                     \
+  attn_fwd_f32_kernel<HDV, false><<<grid, lp.block, lp.smem, stream>>>(qkv, dst_rowptr, dst_src, nullptr, \
+      inv_deg, agg, lse, F, d, H, hd, lp.tile, scale)
+  AMPCONV_DISPATCH_HD(hd, CALL)
+#undef CALL
+  AMPCONV_CHECK_LAUNCH();
+  return AMPCONV_OK;
+}
+
+extern "C" int ampconv_attn_bwd_f32(const float* qkv, const float* d_agg, const float* lse,
+                                    const int32_t* dst_rowptr, const int32_t* dst_src,
+                                    const int32_t* src_rowptr, const int32_t* src_dst, const int32_t* src_pos,
+                                    float* d_qkv, float* delta,
+                                    int64_t N, int64_t E, int F, int d, int H, void* stream_) {
+  AMPCONV_REQUIRE(valid_shape(N, E, F, d, H));
+  if (N == 0) return AMPCONV_OK;
+  AMPCONV_REQUIRE(qkv && d_agg && dst_rowptr && src_rowptr && d_qkv);
+  AMPCONV_REQUIRE(E == 0 || (lse && delta && dst_src && src_dst && src_pos));
+  const int hd = d / H;
+  if (hd > 128) return AMPCONV_ERR_UNSUPPORTED;
+  const float scale = 1.0f / sqrtf((float)hd);
+  cudaStream_t stream = as_stream(stream_);
+  {
+    LaunchPlan lp = plan_rows(F, H, hd, 2);
+    dim3 grid((unsigned)N, (unsigned)lp.row_blocks);
+#define CALL(HDV)                                                                                   \
+  attn_bwd_dq_f32_kernel<HDV><<<grid, lp.block, lp.smem, stream>>>(qkv, d_agg, lse, dst_rowptr, dst_src, \
+      d_qkv, delta, F, d, H, hd, lp.tile, scale)
+    AMPCONV_DISPATCH_HD(hd, CALL)
+#undef CALL
+    AMPCONV_CHECK_LAUNCH();
+  }
+  {
+    LaunchPlan lp = plan_rows(F, H, hd, 2);
+    const int span = lp.ncols_max / hd;
+    size_t smem = lp.smem + (size_t)2 * span * lp.tile * sizeof(float);
+    dim3 grid((unsigned)N, (unsigned)lp.row_blocks);
+#define CALL(HDV)                                                                                     \
+  attn_bwd_dkv_f32_kernel<HDV><<<grid, lp.block, smem, stream>>>(qkv, d_agg, lse, delta, src_rowptr, src_dst, \
+      src_pos, d_qkv, F, d, H, hd, lp.tile, scale)
+    AMPCONV_DISPATCH_HD(hd, CALL)
+#undef CALL
+    AMPCONV_CHECK_LAUNCH();
+  }
+  return AMPCONV_OK;
+}
+
+extern "C" int ampconv_attn_weights_f32(const float* qkv, const float* lse, const int32_t* dst_rowptr,
+                                        const int32_t* dst_src, const int32_t* dst_eid, float* weights,
+                                        int64_t N, int64_t E, int F, int d, int H, void* stream_) {
+  AMPCONV_REQUIRE(valid_shape(N, E, F, d, H));
+  if (E == 0) return AMPCONV_OK;
+  AMPCONV_REQUIRE(qkv && lse && dst_rowptr && dst_src && dst_eid && weights);
+  const int hd = d / H;
+  cudaStream_t stream = as_stream(stream_);
+  // slot -> destination map lives at the tail of `weights`?  No: recompute into a small scratch
+  // carved from the caller's weights buffer is not possible, so it is allocated on the stream.
+  int32_t* slot_dst = nullptr;
+  AMPCONV_CUDA_TRY(cudaMallocAsync((void**)&slot_dst, (size_t)E * sizeof(int32_t), stream));
+  slot_dst_kernel<<<(unsigned)ceil_div<int64_t>(N, 256), 256, 0, stream>>>(dst_rowptr, N, slot_dst);
+  const int tiles = (F + 15) / 16;
+  dim3 grid((unsigned)E, (unsigned)(tiles * tiles));
+  size_t smem = (size_t)2 * 16 * (hd + 1) * sizeof(float);
+  attn_weights_f32_kernel<<<grid, 256, smem, stream>>>(qkv, lse, slot_dst, dst_src, dst_eid, weights, F, d, H,
+                                                      1.0f / sqrtf((float)hd));
+  cudaError_t le = cudaGetLastError();
+  cudaFreeAsync(slot_dst, stream);
+  if (le != cudaSuccess) return cuda_fail(le);
+  return AMPCONV_OK;
+}
+
+extern "C" int ampconv_edge_output_f32(const float* qkv, const float* lse, const int32_t* dst_rowptr,
+                                       const int32_t* dst_src, const int32_t* dst_eid,
+                                       const float* out_proj_weight, const float* out_proj_bias,
+                                       float* edge_out, int64_t N, int64_t E, int F, int d, int H, void* stream_) {
+  (void)lse;
+  AMPCONV_REQUIRE(valid_shape(N, E, F, d, H));
+  if (E == 0) return AMPCONV_OK;
+  AMPCONV_REQUIRE(qkv && dst_rowptr && dst_src && dst_eid && out_proj_weight && out_proj_bias && edge_out);
+  const int hd = d / H;
+  if (hd > 128) return AMPCONV_ERR_UNSUPPORTED;
+  cudaStream_t stream = as_stream(stream_);
+  float* pre = nullptr;   // per-edge attention output before out_proj
+  const size_t bytes = (size_t)E * F * d * sizeof(float);
+  AMPCONV_CUDA_TRY(cudaMallocAsync((void**)&pre, bytes, stream));
+  LaunchPlan lp = plan_rows(F, H, hd, 2);
+  dim3 grid((unsigned)N, (unsigned)lp.row_blocks);
+  const float scale = 1.0f / sqrtf((float)hd);
+#define CALL(HDV)                                                                                    \
+  attn_fwd_f32_kernel<HDV, true><<<grid, lp.block, lp.smem, stream>>>(qkv, dst_rowptr, dst_src, dst_eid, \
+      nullptr, pre, nullptr, F, d, H, hd, lp.tile, scale)
+  AMPCONV_DISPATCH_HD(hd, CALL)
+#undef CALL
+  cudaError_t le = cudaGetLastError();
+  int rc = AMPCONV_OK;
+  if (le != cudaSuccess) {
+    rc = cuda_fail(le);
+  } else {
+    GemmEpilogue epi;
+    epi.bias = out_proj_bias;
+    rc = gemm_f32(pre, d, 1, out_proj_weight, 1, d, edge_out, d, (int64_t)E * F, d, d, epi, 1, nullptr, stream);
+  }
+  cudaFreeAsync(pre, stream);
+  return rc;
+}

@@ -1,0 +1,147 @@
+"""autograd glue between torch tensors and the C ABI (include/ampconv.h).
+
+``amp_conv(x, graph, in_proj_weight, in_proj_bias, out_proj_weight, out_proj_bias, num_heads)``
+computes what the reference's ``AMPConv.forward`` computes (``src/ampnet/conv/amp_conv.py:24-51``)
+and is differentiable w.r.t. ``x`` and the four parameters.  All launches go to the current CUDA
+stream; nothing here synchronises.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+MODES = ("fp32",)
+
+
+def _stream(dev):
+    return _lib.stream_ptr(torch.cuda.current_stream(dev))
+
+
+def _param_grad_ws(out_dim, in_dim, dev):
+    nbytes = ctypes.c_size_t(0)
+    _lib.call("ampconv_param_grad_workspace_bytes", _lib.i32(out_dim), _lib.i32(in_dim), ctypes.byref(nbytes))
+    return torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+
+
+class _Saved:
+    """What the last forward of a layer keeps for backward and for the lazy side outputs."""
+
+    def __init__(self, mode, graph, shape, qkv, agg, lse):
+        self.mode, self.graph, self.shape = mode, graph, shape
+        self.qkv, self.agg, self.lse = qkv, agg, lse
+
+
+def _forward_fp32(x, graph, w_in, b_in, w_out, b_out, num_heads):
+    n, width = x.shape
+    d = w_in.shape[1]
+    f = width // d
+    dev = x.device
+    e = graph.num_edges
+    st = _stream(dev)
+    rows = n * f
+    qkv = torch.empty((rows, 3 * d), dtype=torch.float32, device=dev)
+    agg = torch.empty((rows, d), dtype=torch.float32, device=dev)
+    lse = torch.empty((e, num_heads, f), dtype=torch.float32, device=dev)
+    out = torch.empty((n, width), dtype=torch.float32, device=dev)
+    _lib.call("ampconv_qkv_proj_f32", x, w_in, b_in, qkv, _lib.i64(rows), _lib.i32(d), st)
+    _lib.call("ampconv_attn_fwd_f32", qkv, graph.dst_rowptr, graph.dst_src, graph.inv_deg, agg, lse,
+              _lib.i64(n), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(num_heads), st)
+    _lib.call("ampconv_out_proj_f32", agg, w_out, b_out, graph.has_in, out,
+              _lib.i64(n), _lib.i32(f), _lib.i32(d), st)
+    return out, _Saved("fp32", graph, (n, e, f, d, num_heads), qkv, agg, lse)
+
+
+def _backward_fp32(saved, x, w_in, w_out, d_out):
+    n, e, f, d, h = saved.shape
+    g = saved.graph
+    dev = x.device
+    st = _stream(dev)
+    rows = n * f
+    d_out = d_out.contiguous()
+    d_agg = torch.empty((rows, d), dtype=torch.float32, device=dev)
+    d_w_out = torch.empty_like(w_out)
+    d_b_out = torch.empty(d, dtype=torch.float32, device=dev)
+    ws = _param_grad_ws(3 * d, d, dev)
+    _lib.call("ampconv_out_proj_bwd_f32", d_out, saved.agg, w_out, g.inv_deg, g.has_in,
+              d_agg, d_w_out, d_b_out, _lib.i64(n), _lib.i32(f), _lib.i32(d),
+              ws, _lib.size_t(ws.numel()), st)
+    d_qkv = torch.empty((rows, 3 * d), dtype=torch.float32, device=dev)
+    delta = torch.empty_like(saved.lse)
+    _lib.call("ampconv_attn_bwd_f32", saved.qkv, d_agg, saved.lse, g.dst_rowptr, g.dst_src,
+              g.src_rowptr, g.src_dst, g.src_pos, d_qkv, delta,
+              _lib.i64(n), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(h), st)
+    d_x = torch.empty_like(x)
+    d_w_in = torch.empty_like(w_in)
+    d_b_in = torch.empty(3 * d, dtype=torch.float32, device=dev)
+    _lib.call("ampconv_qkv_proj_bwd_f32", x, d_qkv, w_in, d_x, d_w_in, d_b_in,
+              _lib.i64(rows), _lib.i32(d), ws, _lib.size_t(ws.numel()), st)
+    return d_x, d_w_in, d_b_in, d_w_out, d_b_out
+
+
+class _AMPConvFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w_in, b_in, w_out, b_out, graph, num_heads, mode, holder):
+        with torch.cuda.device(x.device):
+            out, saved = _forward_fp32(x, graph, w_in, b_in, w_out, b_out, num_heads)
+        ctx.save_for_backward(x, w_in, w_out)
+        ctx.saved_state = saved
+        if holder is not None:
+            holder["saved"] = saved
+            holder["params"] = (w_out.detach(), b_out.detach())
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x, w_in, w_out = ctx.saved_tensors
+        with torch.cuda.device(x.device):
+            d_x, d_w_in, d_b_in, d_w_out, d_b_out = _backward_fp32(ctx.saved_state, x, w_in, w_out, d_out)
+        return d_x, d_w_in, d_b_in, d_w_out, d_b_out, None, None, None, None
+
+
+def check_inputs(x, edge_index, embed_dim, num_heads):
+    if x.dim() != 2:
+        raise ValueError("x must have shape [N, F * embed_dim]")
+    if x.shape[1] % embed_dim != 0:
+        # the reference prints "Error, invalid configuration" and then fails in reshape (amp_conv.py:32-36)
+        raise ValueError(f"invalid configuration: x.shape[1]={x.shape[1]} is not a multiple of embed_dim={embed_dim}")
+    if embed_dim % num_heads != 0:
+        raise ValueError("embed_dim must be divisible by num_heads")
+    if not x.is_cuda:
+        raise TypeError("ampnet_b200.AMPConv has no CPU path: x must be a CUDA tensor "
+                        "(the CPU oracle is oracle/torch_port.py and is test infrastructure only)")
+    if x.dtype != torch.float32:
+        raise TypeError("x must be float32, like the reference's activations")
+    if edge_index.device != x.device:
+        raise TypeError("x and edge_index must be on the same device")
+
+
+def amp_conv(x, graph, w_in, b_in, w_out, b_out, num_heads, mode="fp32", holder=None):
+    if mode not in MODES:
+        raise ValueError(f"unknown mode {mode!r}; available: {MODES}")
+    return _AMPConvFunction.apply(x.contiguous(), w_in.contiguous(), b_in.contiguous(), w_out.contiguous(),
+                                  b_out.contiguous(), graph, num_heads, mode, holder)
+
+
+def attention_weights(saved):
+    """Head-averaged coefficients [E, F, F] in original edge order (``attn_output_weights``)."""
+    n, e, f, d, h = saved.shape
+    g = saved.graph
+    dev = saved.qkv.device
+    w = torch.empty((e, f, f), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("ampconv_attn_weights_f32", saved.qkv, saved.lse, g.dst_rowptr, g.dst_src, g.dst_eid, w,
+                  _lib.i64(n), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(h), _stream(dev))
+    return w
+
+
+def edge_output(saved, w_out, b_out):
+    """Per-edge attention output after out_proj [E, F, d] in original edge order (``attn_output``)."""
+    n, e, f, d, h = saved.shape
+    g = saved.graph
+    dev = saved.qkv.device
+    o = torch.empty((e, f, d), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("ampconv_edge_output_f32", saved.qkv, saved.lse, g.dst_rowptr, g.dst_src, g.dst_eid,
+                  w_out, b_out, o, _lib.i64(n), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(h), _stream(dev))
+    return o

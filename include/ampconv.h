@@ -1,0 +1,144 @@
+/*
+ * ampconv.h -- C ABI of the B200-native AMPConv hot path (libampconv.so).
+ *
+ * The reference (HarryL-Git/ampnet) has no FFI: its "operator API" for this path is the
+ * PyTorch module AMPConv (src/ampnet/conv/amp_conv.py:9-51), which dispatches to PyG's
+ * MessagePassing.propagate (gather x[src], x[dst]; scatter-mean at dst) and to
+ * torch.nn.MultiheadAttention.  This header is what a host -- the Python mirror in
+ * ampnet_b200/, or any other language with a C FFI -- binds instead of that eager chain.
+ * Every entry point cites the reference step it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - every call returns 0 on success or a negative ampconv_status; nothing throws; the
+ *     caller owns every buffer (the two opt-in side-output calls, ampconv_attn_weights_* and
+ *     ampconv_edge_output_*, use stream-ordered temporaries); nothing synchronises the device
+ *     except ampconv_graph_build (which must report out-of-range indices);
+ *   - tokens per node F = width / d, head_dim hd = d / H, rows = N * F;
+ *   - "position" p in [0,E) is an edge's slot in DESTINATION-sorted order (stable).
+ */
+#ifndef AMPCONV_H_
+#define AMPCONV_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMPCONV_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define AMPCONV_API __attribute__((visibility("default")))
+#else
+#define AMPCONV_API
+#endif
+
+typedef enum ampconv_status {
+  AMPCONV_OK = 0,
+  AMPCONV_ERR_INVALID_ARGUMENT = -1, /* null pointer, negative size, d % H != 0 ...           */
+  AMPCONV_ERR_UNSUPPORTED = -2,      /* shape outside what the requested kernel family covers  */
+  AMPCONV_ERR_INDEX_RANGE = -3,      /* edge_index holds a node id outside [0, N)              */
+  AMPCONV_ERR_WORKSPACE = -4,        /* workspace too small                                    */
+  AMPCONV_ERR_CUDA = -5,             /* a CUDA runtime call or launch failed (see last_cuda)   */
+  AMPCONV_ERR_NO_DEVICE = -6         /* no sm_100 device                                       */
+} ampconv_status;
+
+AMPCONV_API int ampconv_abi_version(void);
+AMPCONV_API const char* ampconv_strerror(int status);
+/* cudaError_t of the most recent AMPCONV_ERR_CUDA on this thread (0 if none). */
+AMPCONV_API int ampconv_last_cuda_error(void);
+/* Fills SM count and compute capability of the current device. */
+AMPCONV_API int ampconv_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * Graph preparation.  Replaces the per-call bookkeeping of PyG propagate
+ * (amp_conv.py:24-26: x_j = x[edge_index[0]], x_i = x[edge_index[1]], scatter-mean at
+ * edge_index[1]) by two sorted views that are built once per edge_index and reused by both
+ * layers and by forward and backward:
+ *   by destination: dst_rowptr[N+1], dst_src[E] (source of the edge in slot p),
+ *                   dst_eid[E]  (column of edge_index the slot came from);
+ *   by source:      src_rowptr[N+1], src_dst[E], src_pos[E] (destination-sorted slot of the
+ *                   same edge, to find its saved softmax statistics);
+ *   inv_deg[N] = 1 / max(in_degree, 1), has_in[N] = in_degree > 0 ? 1 : 0.
+ * Duplicate edges and self loops are ordinary edges.  Synchronises `stream`.
+ * ------------------------------------------------------------------------------------------ */
+AMPCONV_API int ampconv_graph_workspace_bytes(int64_t num_edges, int64_t num_nodes, size_t* bytes);
+AMPCONV_API int ampconv_graph_build(const int64_t* edge_index /* [2,E] row 0 = src, row 1 = dst */,
+                        int64_t num_edges, int64_t num_nodes,
+                        int32_t* dst_rowptr, int32_t* dst_src, int32_t* dst_eid,
+                        int32_t* src_rowptr, int32_t* src_dst, int32_t* src_pos,
+                        float* inv_deg, float* has_in,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Strict fp32 family (CUDA cores, any F / d / H with hd <= 128).  Parity bar 1e-4 relative.
+ * ------------------------------------------------------------------------------------------ */
+
+/* qkv[r, 0:3d] = x[r, 0:d] @ in_proj_weight^T + in_proj_bias, once per NODE token instead of
+ * once per edge (replaces F._in_projection_packed on [E,F,d] gathers;
+ * custom_multihead_attn_forward.py:4031-4084). */
+AMPCONV_API int ampconv_qkv_proj_f32(const float* x, const float* in_proj_weight, const float* in_proj_bias,
+                         float* qkv, int64_t rows, int d, void* stream);
+
+/* Fused per-edge multi-head attention + mean aggregation, destination-sorted, no atomics
+ * (replaces head split, q*hd^-1/2, bmm, softmax, bmm of custom_multihead_attn_forward.py
+ * :4140-4186,4376-4387 and PyG's scatter-mean, amp_conv.py:11).
+ *   agg[n,i,:]  = inv_deg[n] * sum over in-edges of softmax_j(q_i k_j / sqrt(hd)) v_j
+ *   lse[p,h,i]  = log-sum-exp of the scaled scores of edge slot p (saved for backward). */
+AMPCONV_API int ampconv_attn_fwd_f32(const float* qkv, const int32_t* dst_rowptr, const int32_t* dst_src,
+                         const float* inv_deg, float* agg, float* lse,
+                         int64_t num_nodes, int64_t num_edges, int F, int d, int H, void* stream);
+
+/* out[r,:] = agg[r,:] @ out_proj_weight^T + out_proj_bias * has_in[node(r)]
+ * (out_proj of custom_multihead_attn_forward.py:4436-4437, moved after the mean). */
+AMPCONV_API int ampconv_out_proj_f32(const float* agg, const float* out_proj_weight, const float* out_proj_bias,
+                         const float* has_in, float* out, int64_t num_nodes, int F, int d, void* stream);
+
+/* Head-averaged attention coefficients in ORIGINAL edge order (the attn_output_weights side
+ * output, amp_conv.py:39; custom_multihead_attn_forward.py:4441-4442):
+ *   weights[dst_eid[p], i, j] = mean_h exp(q_i k_j / sqrt(hd) - lse[p,h,i]). */
+AMPCONV_API int ampconv_attn_weights_f32(const float* qkv, const float* lse, const int32_t* dst_rowptr,
+                             const int32_t* dst_src, const int32_t* dst_eid, float* weights,
+                             int64_t num_nodes, int64_t num_edges, int F, int d, int H, void* stream);
+
+/* Per-edge attention output after out_proj in ORIGINAL edge order (the attn_output side output,
+ * amp_conv.py:39): edge_out[dst_eid[p], i, :] = (softmax(q k^T) v)[i,:] @ Wo^T + bo. */
+AMPCONV_API int ampconv_edge_output_f32(const float* qkv, const float* lse, const int32_t* dst_rowptr,
+                            const int32_t* dst_src, const int32_t* dst_eid,
+                            const float* out_proj_weight, const float* out_proj_bias, float* edge_out,
+                            int64_t num_nodes, int64_t num_edges, int F, int d, int H, void* stream);
+
+/* Backward of ampconv_out_proj_f32.  d_agg is additionally multiplied by inv_deg[node], i.e. it
+ * is the gradient w.r.t. every in-edge's un-normalised attention output.
+ * d_w [d,d], d_b [d] are overwritten.  workspace: ampconv_param_grad_workspace_bytes(d, d). */
+AMPCONV_API int ampconv_out_proj_bwd_f32(const float* d_out, const float* agg, const float* out_proj_weight,
+                             const float* inv_deg, const float* has_in,
+                             float* d_agg, float* d_w, float* d_b,
+                             int64_t num_nodes, int F, int d,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of ampconv_attn_fwd_f32 (flash-style recompute from lse; autograd of
+ * custom_multihead_attn_forward.py:4140-4186 + scatter-mean).  Two passes, no atomics:
+ * destination-sorted (d_q, delta[p,h,i] = sum_j P dP) then source-sorted (d_k, d_v).
+ * d_qkv [rows,3d] is overwritten; delta is scratch of the size of lse. */
+AMPCONV_API int ampconv_attn_bwd_f32(const float* qkv, const float* d_agg, const float* lse,
+                         const int32_t* dst_rowptr, const int32_t* dst_src,
+                         const int32_t* src_rowptr, const int32_t* src_dst, const int32_t* src_pos,
+                         float* d_qkv, float* delta,
+                         int64_t num_nodes, int64_t num_edges, int F, int d, int H, void* stream);
+
+/* Backward of ampconv_qkv_proj_f32: d_x [rows,d], d_w [3d,d], d_b [3d] are overwritten.
+ * workspace: ampconv_param_grad_workspace_bytes(3d, d). */
+AMPCONV_API int ampconv_qkv_proj_bwd_f32(const float* x, const float* d_qkv, const float* in_proj_weight,
+                             float* d_x, float* d_w, float* d_b, int64_t rows, int d,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+AMPCONV_API int ampconv_param_grad_workspace_bytes(int out_dim, int in_dim, size_t* bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMPCONV_H_ */
