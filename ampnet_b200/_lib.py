@@ -60,6 +60,12 @@ def call(name, *args):
     return status
 
 
+def launch_count():
+    lib = load()
+    lib.ampconv_launch_count.restype = ctypes.c_uint64
+    return int(lib.ampconv_launch_count())
+
+
 def i64(v):
     return ctypes.c_int64(int(v))
 

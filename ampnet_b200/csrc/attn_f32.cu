@@ -429,42 +429,61 @@ extern "C" int ampconv_attn_fwd_f32(const float* qkv, const int32_t* dst_rowptr,
   return AMPCONV_OK;
 }
 
+extern "C" int ampconv_attn_bwd_dq_f32(const float* qkv, const float* d_agg, const float* lse,
+                                       const int32_t* dst_rowptr, const int32_t* dst_src,
+                                       float* d_qkv, float* delta,
+                                       int64_t N, int64_t E, int F, int d, int H, void* stream_) {
+  AMPCONV_REQUIRE(valid_shape(N, E, F, d, H));
+  if (N == 0) return AMPCONV_OK;
+  AMPCONV_REQUIRE(qkv && d_agg && dst_rowptr && d_qkv);
+  AMPCONV_REQUIRE(E == 0 || (lse && delta && dst_src));
+  const int hd = d / H;
+  if (hd > 128) return AMPCONV_ERR_UNSUPPORTED;
+  const float scale = 1.0f / sqrtf((float)hd);
+  cudaStream_t stream = as_stream(stream_);
+  LaunchPlan lp = plan_rows(F, H, hd, 2);
+  dim3 grid((unsigned)N, (unsigned)lp.row_blocks);
+#define CALL(HDV)                                                                                   \
+  attn_bwd_dq_f32_kernel<HDV><<<grid, lp.block, lp.smem, stream>>>(qkv, d_agg, lse, dst_rowptr, dst_src, \
+      d_qkv, delta, F, d, H, hd, lp.tile, scale)
+  AMPCONV_DISPATCH_HD(hd, CALL)
+#undef CALL
+  AMPCONV_CHECK_LAUNCH();
+  return AMPCONV_OK;
+}
+
+extern "C" int ampconv_attn_bwd_dkv_f32(const float* qkv, const float* d_agg, const float* lse, const float* delta,
+                                        const int32_t* src_rowptr, const int32_t* src_dst, const int32_t* src_pos,
+                                        float* d_qkv, int64_t N, int64_t E, int F, int d, int H, void* stream_) {
+  AMPCONV_REQUIRE(valid_shape(N, E, F, d, H));
+  if (N == 0) return AMPCONV_OK;
+  AMPCONV_REQUIRE(qkv && d_agg && src_rowptr && d_qkv);
+  AMPCONV_REQUIRE(E == 0 || (lse && delta && src_dst && src_pos));
+  const int hd = d / H;
+  if (hd > 128) return AMPCONV_ERR_UNSUPPORTED;
+  const float scale = 1.0f / sqrtf((float)hd);
+  cudaStream_t stream = as_stream(stream_);
+  LaunchPlan lp = plan_rows(F, H, hd, 2);
+  const int span = lp.ncols_max / hd;
+  size_t smem = lp.smem + (size_t)2 * span * lp.tile * sizeof(float);
+  dim3 grid((unsigned)N, (unsigned)lp.row_blocks);
+#define CALL(HDV)                                                                                     \
+  attn_bwd_dkv_f32_kernel<HDV><<<grid, lp.block, smem, stream>>>(qkv, d_agg, lse, delta, src_rowptr, src_dst, \
+      src_pos, d_qkv, F, d, H, hd, lp.tile, scale)
+  AMPCONV_DISPATCH_HD(hd, CALL)
+#undef CALL
+  AMPCONV_CHECK_LAUNCH();
+  return AMPCONV_OK;
+}
+
 extern "C" int ampconv_attn_bwd_f32(const float* qkv, const float* d_agg, const float* lse,
                                     const int32_t* dst_rowptr, const int32_t* dst_src,
                                     const int32_t* src_rowptr, const int32_t* src_dst, const int32_t* src_pos,
                                     float* d_qkv, float* delta,
                                     int64_t N, int64_t E, int F, int d, int H, void* stream_) {
-  AMPCONV_REQUIRE(valid_shape(N, E, F, d, H));
-  if (N == 0) return AMPCONV_OK;
-  AMPCONV_REQUIRE(qkv && d_agg && dst_rowptr && src_rowptr && d_qkv);
-  AMPCONV_REQUIRE(E == 0 || (lse && delta && dst_src && src_dst && src_pos));
-  const int hd = d / H;
-  if (hd > 128) return AMPCONV_ERR_UNSUPPORTED;
-  const float scale = 1.0f / sqrtf((float)hd);
-  cudaStream_t stream = as_stream(stream_);
-  {
-    LaunchPlan lp = plan_rows(F, H, hd, 2);
-    dim3 grid((unsigned)N, (unsigned)lp.row_blocks);
-#define CALL(HDV)                                                                                   \
-  attn_bwd_dq_f32_kernel<HDV><<<grid, lp.block, lp.smem, stream>>>(qkv, d_agg, lse, dst_rowptr, dst_src, \
-      d_qkv, delta, F, d, H, hd, lp.tile, scale)
-    AMPCONV_DISPATCH_HD(hd, CALL)
-#undef CALL
-    AMPCONV_CHECK_LAUNCH();
-  }
-  {
-    LaunchPlan lp = plan_rows(F, H, hd, 2);
-    const int span = lp.ncols_max / hd;
-    size_t smem = lp.smem + (size_t)2 * span * lp.tile * sizeof(float);
-    dim3 grid((unsigned)N, (unsigned)lp.row_blocks);
-#define CALL(HDV)                                                                                     \
-  attn_bwd_dkv_f32_kernel<HDV><<<grid, lp.block, smem, stream>>>(qkv, d_agg, lse, delta, src_rowptr, src_dst, \
-      src_pos, d_qkv, F, d, H, hd, lp.tile, scale)
-    AMPCONV_DISPATCH_HD(hd, CALL)
-#undef CALL
-    AMPCONV_CHECK_LAUNCH();
-  }
-  return AMPCONV_OK;
+  int rc = ampconv_attn_bwd_dq_f32(qkv, d_agg, lse, dst_rowptr, dst_src, d_qkv, delta, N, E, F, d, H, stream_);
+  if (rc != AMPCONV_OK) return rc;
+  return ampconv_attn_bwd_dkv_f32(qkv, d_agg, lse, delta, src_rowptr, src_dst, src_pos, d_qkv, N, E, F, d, H, stream_);
 }
 
 extern "C" int ampconv_attn_weights_f32(const float* qkv, const float* lse, const int32_t* dst_rowptr,

@@ -8,6 +8,7 @@
 namespace ampconv {
 
 extern thread_local int g_last_cuda_error;
+extern unsigned long long g_launch_count;   // kernels launched by this library (bench.py's gpu_launches)
 
 inline int cuda_fail(cudaError_t e) {
   g_last_cuda_error = static_cast<int>(e);
@@ -22,6 +23,7 @@ inline int cuda_fail(cudaError_t e) {
 
 #define AMPCONV_CHECK_LAUNCH()                                   \
   do {                                                           \
+    ++::ampconv::g_launch_count;                                 \
     cudaError_t _e = cudaGetLastError();                         \
     if (_e != cudaSuccess) return ::ampconv::cuda_fail(_e);      \
   } while (0)

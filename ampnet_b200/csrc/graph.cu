@@ -8,6 +8,7 @@
 namespace ampconv {
 
 thread_local int g_last_cuda_error = 0;
+unsigned long long g_launch_count = 0;
 
 int sm_count() {
   static int cached = 0;
@@ -115,6 +116,8 @@ extern "C" const char* ampconv_strerror(int status) {
 }
 
 extern "C" int ampconv_last_cuda_error(void) { return g_last_cuda_error; }
+
+extern "C" uint64_t ampconv_launch_count(void) { return g_launch_count; }
 
 extern "C" int ampconv_device_info(int* sm, int* cc_major, int* cc_minor) {
   AMPCONV_REQUIRE(sm && cc_major && cc_minor);

@@ -68,9 +68,10 @@ def _backward_fp32(saved, x, w_in, w_out, d_out):
               ws, _lib.size_t(ws.numel()), st)
     d_qkv = torch.empty((rows, 3 * d), dtype=torch.float32, device=dev)
     delta = torch.empty_like(saved.lse)
-    _lib.call("ampconv_attn_bwd_f32", saved.qkv, d_agg, saved.lse, g.dst_rowptr, g.dst_src,
-              g.src_rowptr, g.src_dst, g.src_pos, d_qkv, delta,
-              _lib.i64(n), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(h), st)
+    dims = (_lib.i64(n), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(h), st)
+    _lib.call("ampconv_attn_bwd_dq_f32", saved.qkv, d_agg, saved.lse, g.dst_rowptr, g.dst_src, d_qkv, delta, *dims)
+    _lib.call("ampconv_attn_bwd_dkv_f32", saved.qkv, d_agg, saved.lse, delta, g.src_rowptr, g.src_dst, g.src_pos,
+              d_qkv, *dims)
     d_x = torch.empty_like(x)
     d_w_in = torch.empty_like(w_in)
     d_b_in = torch.empty(3 * d, dtype=torch.float32, device=dev)

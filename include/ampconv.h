@@ -50,6 +50,8 @@ AMPCONV_API int ampconv_abi_version(void);
 AMPCONV_API const char* ampconv_strerror(int status);
 /* cudaError_t of the most recent AMPCONV_ERR_CUDA on this thread (0 if none). */
 AMPCONV_API int ampconv_last_cuda_error(void);
+/* Number of kernels this library has launched so far in this process (monotonic). */
+AMPCONV_API uint64_t ampconv_launch_count(void);
 /* Fills SM count and compute capability of the current device. */
 AMPCONV_API int ampconv_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
@@ -121,9 +123,18 @@ AMPCONV_API int ampconv_out_proj_bwd_f32(const float* d_out, const float* agg, c
                              void* workspace, size_t workspace_bytes, void* stream);
 
 /* Backward of ampconv_attn_fwd_f32 (flash-style recompute from lse; autograd of
- * custom_multihead_attn_forward.py:4140-4186 + scatter-mean).  Two passes, no atomics:
- * destination-sorted (d_q, delta[p,h,i] = sum_j P dP) then source-sorted (d_k, d_v).
- * d_qkv [rows,3d] is overwritten; delta is scratch of the size of lse. */
+ * custom_multihead_attn_forward.py:4140-4186 + scatter-mean).  Two kernels, no atomics:
+ *   _dq : destination-sorted; writes d_qkv[:, 0:d] and delta[p,h,i] = sum_j P_ij dP_ij;
+ *   _dkv: source-sorted; reads delta; writes d_qkv[:, d:3d].
+ * ampconv_attn_bwd_f32 runs both.  d_qkv [rows,3d] is overwritten; delta has the size of lse. */
+AMPCONV_API int ampconv_attn_bwd_dq_f32(const float* qkv, const float* d_agg, const float* lse,
+                            const int32_t* dst_rowptr, const int32_t* dst_src,
+                            float* d_qkv, float* delta,
+                            int64_t num_nodes, int64_t num_edges, int F, int d, int H, void* stream);
+AMPCONV_API int ampconv_attn_bwd_dkv_f32(const float* qkv, const float* d_agg, const float* lse, const float* delta,
+                             const int32_t* src_rowptr, const int32_t* src_dst, const int32_t* src_pos,
+                             float* d_qkv,
+                             int64_t num_nodes, int64_t num_edges, int F, int d, int H, void* stream);
 AMPCONV_API int ampconv_attn_bwd_f32(const float* qkv, const float* d_agg, const float* lse,
                          const int32_t* dst_rowptr, const int32_t* dst_src,
                          const int32_t* src_rowptr, const int32_t* src_dst, const int32_t* src_pos,
