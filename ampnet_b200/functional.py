@@ -146,3 +146,46 @@ def edge_output(saved, w_out, b_out):
         _lib.call("ampconv_edge_output_f32", saved.qkv, saved.lse, g.dst_rowptr, g.dst_src, g.dst_eid,
                   w_out, b_out, o, _lib.i64(n), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(h), _stream(dev))
     return o
+
+
+def profile_stages(x, graph, w_in, b_in, w_out, b_out, num_heads, d_out, mode, reps):
+    """Per-kernel durations (ms) of the three attention kernels, each timed alone with CUDA events on
+    the stream it is launched on (used by bench.py for the roofline line)."""
+    n, width = x.shape
+    d = w_in.shape[1]
+    f = width // d
+    dev = x.device
+    e = graph.num_edges
+    rows = n * f
+    with torch.cuda.device(dev):
+        st = _stream(dev)
+        out, saved = _forward_fp32(x, graph, w_in, b_in, w_out, b_out, num_heads)
+        d_agg = torch.empty((rows, d), dtype=torch.float32, device=dev)
+        d_w_out = torch.empty_like(w_out)
+        d_b_out = torch.empty(d, dtype=torch.float32, device=dev)
+        ws = _param_grad_ws(3 * d, d, dev)
+        _lib.call("ampconv_out_proj_bwd_f32", d_out.contiguous(), saved.agg, w_out, graph.inv_deg, graph.has_in,
+                  d_agg, d_w_out, d_b_out, _lib.i64(n), _lib.i32(f), _lib.i32(d), ws, _lib.size_t(ws.numel()), st)
+        d_qkv = torch.empty((rows, 3 * d), dtype=torch.float32, device=dev)
+        delta = torch.empty_like(saved.lse)
+        dims = (_lib.i64(n), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(num_heads), st)
+        calls = {
+            "attn_fwd": lambda: _lib.call("ampconv_attn_fwd_f32", saved.qkv, graph.dst_rowptr, graph.dst_src,
+                                          graph.inv_deg, saved.agg, saved.lse, *dims),
+            "attn_bwd_dq": lambda: _lib.call("ampconv_attn_bwd_dq_f32", saved.qkv, d_agg, saved.lse, graph.dst_rowptr,
+                                             graph.dst_src, d_qkv, delta, *dims),
+            "attn_bwd_dkv": lambda: _lib.call("ampconv_attn_bwd_dkv_f32", saved.qkv, d_agg, saved.lse, delta,
+                                              graph.src_rowptr, graph.src_dst, graph.src_pos, d_qkv, *dims),
+        }
+        result = {}
+        for name, fn in calls.items():
+            fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            result[name] = e0.elapsed_time(e1) / reps
+    return result

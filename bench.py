@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- AMPConv fwd+bwd edges/sec on B200 (BASELINE.json metric), driver contract.
+
+    python bench.py --gpus 1 --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+
+A "step" is one forward + backward of one AMPConv layer over the whole synthetic graph
+(loss = (out * d_out).sum()).  At N=1 the workload is config C4 of SURVEY.md section 8 (synthetic
+ogbn-arxiv shape: 169 343 nodes, 1 166 243 edges, 128 feature tokens, embed 64, 4 heads), the
+largest configuration of BASELINE.json that fits one GPU.  Inputs are larger than L2 (x alone is
+5.5 GB), so no explicit L2 flush is needed between iterations.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: N, E, F, d, H  
+    "C4": dict(n=169343, e=1166243, f=128, d=64, h=4, desc="synthetic ogbn-arxiv shape, full graph"),
+    "C2": dict(n=750, e=3000, f=20, d=128, h=4, desc="GraphSAINT-Cora subgraph shape"),
+    "C3": dict(n=400, e=8400, f=2, d=3, h=1, desc="XOR graph shape"),
+    "C4s": dict(n=16934, e=116624, f=128, d=64, h=4, desc="C4 token shape at 1/10 of the nodes and edges"),
+}
+METRIC = "AMPConv fwd+bwd edges/sec"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=float(p["hbm_gbs"]), bf16_tflops=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                    source="MEASURED_PEAKS.json")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for name, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_problem(spec, graph_kind, seed=1234):
+    """Synthetic inputs of SURVEY.md section 8(d): x ~ N(0,1), d_out ~ N(0,1), uniform or skewed graph."""
+    from oracle import cases  # input generator only (numpy); no reference/oracle compute involved
+    return cases.make_graph(graph_kind, spec["n"], spec["e"], seed=7 + seed)
+
+
+def init_conv(conv, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    mha = conv.multi_head_attention
+    with torch.no_grad():
+        d = conv.embed_dim
+        bound = (6.0 / (4 * d)) ** 0.5
+        mha.in_proj_weight.copy_((torch.rand(3 * d, d, generator=g) * 2 - 1) * bound)
+        mha.in_proj_bias.copy_(0.1 * torch.randn(3 * d, generator=g))
+        mha.out_proj.weight.copy_((torch.rand(d, d, generator=g) * 2 - 1) / d ** 0.5)
+        mha.out_proj.bias.copy_(0.1 * torch.randn(d, generator=g))
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the reference's eager op chain (oracle/torch_port.py) on a bounded edge sample
+# ------------------------------------------------------------------------------------------
+def cpu_sample_run(spec, sample_edges, sample_nodes, reps, warmup):
+    from oracle import cases
+    from oracle.torch_port import AMPConvPort, fwd_bwd_chunked
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    f, d, h = spec["f"], spec["d"], spec["h"]
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(sample_nodes, f * d, generator=g)
+    d_out = torch.randn(sample_nodes, f * d, generator=g)
+    ei = torch.from_numpy(cases.make_graph("uniform", sample_nodes, sample_edges, seed=7))
+    conv = AMPConvPort(d, h)
+    init_conv(conv)
+    chunk = max(64, min(sample_edges, int(2.5e8 // max(1, h * f * f))))   # keeps [chunk,H,F,F] fp32 near 1 GB
+    times = []
+    for it in range(warmup + reps):
+        conv.zero_grad()
+        t0 = time.perf_counter()
+        fwd_bwd_chunked(conv, x, ei, d_out, chunk)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return dict(times=times, cores=cores, chunk=chunk)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    spec = WORKLOADS[args.workload]
+    se = min(spec["e"], args.cpu_sample_edges)
+    sn = min(spec["n"], max(2, se // 2))
+    r = cpu_sample_run(spec, se, sn, reps=args.steps, warmup=args.warmup)
+    per_step = float(np.mean(r["times"]))
+    value = se / per_step
+    sample = (f"{se} edges over a {sn}-node slice at the {args.workload} token shape "
+              f"(F={spec['f']}, d={spec['d']}, H={spec['h']}), fp32, edge-chunked by {r['chunk']}; edges/s is per-edge linear")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {spec['desc']} (N={spec['n']}, E={spec['e']}, F={spec['f']}, "
+                               f"d={spec['d']}, H={spec['h']})", "graph": "uniform", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "edges/s", "cores": r["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def algorithmic_bytes(spec, mode):
+    """Per-launch algorithmic bytes of the three attention kernels (DESIGN.md 'Kernels')."""
+    n, e, f, d, h = spec["n"], spec["e"], spec["f"], spec["d"], spec["h"]
+    b = 4 if mode == "fp32" else 2
+    tile = f * d * b
+    stat = h * f * 4
+    return {
+        "attn_fwd": e * (2 * tile + 12 + stat) + n * (tile + f * d * 4),
+        "attn_bwd_dq": e * (2 * tile + 12 + 2 * stat) + n * (2 * tile + f * d * 4),
+        "attn_bwd_dkv": e * (2 * tile + 12 + 2 * stat) + n * (2 * tile + 2 * f * d * 4),
+    }
+
+
+def run_ours(args):
+    from ampnet_b200 import AMPConv, _lib
+    from ampnet_b200 import functional as F_
+    from ampnet_b200.graph import Graph, clear_cache
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: ampnet_b200 has no CPU path")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    spec = dict(WORKLOADS[args.workload])
+    n, e, f, d, h = spec["n"], spec["e"], spec["f"], spec["d"], spec["h"]
+
+    # every rank owns an independent graph shard of the workload's shape (weak scaling; see DESIGN.md "Multi-GPU")
+    edge_index_np = make_problem(spec, args.graph, seed=rank)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x_host = torch.empty((n, f * d), dtype=torch.float32, pin_memory=True)
+    x = torch.randn((n, f * d), generator=gen, device=dev)
+    x_host.copy_(x)
+    d_out = torch.randn((n, f * d), generator=gen, device=dev)
+    ei_host = torch.from_numpy(edge_index_np).pin_memory()
+    edge_index = ei_host.to(dev)
+    conv = AMPConv(d, h, mode=args.mode).to(dev)
+    init_conv(conv)
+    params = list(conv.parameters())
+
+    def step(xin, ei):
+        for p in params:
+            p.grad = None
+        xin.grad = None
+        out = conv(xin, ei)
+        loss = (out * d_out).sum()
+        loss.backward()
+        return loss
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    x.requires_grad_(True)
+    for _ in range(args.warmup):
+        step(x, edge_index)
+    barrier()
+    launches0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        ev0.record()
+        for _ in range(args.steps):
+            step(x, edge_index)
+        ev1.record()
+        barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = (_lib.launch_count() - launches0) // max(1, args.steps)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * e / (ms_step * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers: H2D x + edge_index, graph build,
+    #      fwd + bwd, D2H of the loss and the four parameter gradients
+    e2e_steps = max(1, min(args.steps, 3))
+    grads_host = [torch.empty_like(p, device="cpu").pin_memory() for p in params]
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    x_dev = torch.empty_like(x_host, device=dev)
+
+    def e2e_step():
+        clear_cache()
+        x_dev.copy_(x_host, non_blocking=True)
+        ei_dev = ei_host.to(dev, non_blocking=True)
+        xin = x_dev.detach().requires_grad_(True)
+        loss = step(xin, ei_dev)
+        loss_host.copy_(loss.detach(), non_blocking=True)
+        for gh, p in zip(grads_host, params):
+            gh.copy_(p.grad, non_blocking=True)
+
+    del x
+    torch.cuda.empty_cache()
+    e2e_step()
+    barrier()
+    ev0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    ev1.record()
+    barrier()
+    e2e_ms = ev0.elapsed_time(ev1) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    h2d = x_host.numel() * 4 + ei_host.numel() * 8
+    d2h = 4 + sum(p.numel() * 4 for p in params)
+
+    # ---- per-kernel durations of the attention kernels (CUDA events on the launching stream)
+    kern_ms = profile_attention_kernels(conv, x_dev, edge_index, d_out, args.mode, reps=max(2, min(args.steps, 5)))
+    alg = algorithmic_bytes(spec, args.mode)
+    pk = peaks()
+    dominant = max(kern_ms, key=kern_ms.get)
+    achieved = alg[dominant] / (kern_ms[dominant] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                "kernel_ms": kern_ms, "algorithmic_bytes": alg}
+
+    if rank != 0:
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        se = min(spec["e"], args.cpu_sample_edges)
+        sn = min(spec["n"], max(2, se // 2))
+        r = cpu_sample_run(spec, se, sn, reps=2, warmup=1)
+        cpu = {"value": se / float(np.mean(r["times"])), "unit": "edges/s", "cores": r["cores"], "kind": "port",
+               "sample": f"{se} edges over a {sn}-node slice at the {args.workload} token shape, fp32, "
+                         f"reference op chain (oracle/torch_port.py), edge-chunked by {r['chunk']}"}
+    line = {
+        "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32" if args.mode == "fp32" else "bf16", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {spec['desc']} (N={n}, E={e}, F={f}, d={d}, H={h}), one AMPConv layer "
+                               f"fwd+bwd, {args.graph} graph seed 7", "mode": args.mode,
+                   "l2": "inputs larger than L2 (x = %.1f GB); no flush" % (n * f * d * 4 / 1e9),
+                   "parallelism": "1 GPU" if world == 1 else f"{world} independent graph shards (weak scaling)"},
+        "node_updates_per_s": world * n / (ms_step * 1e-3),
+        "clocks": clocks.summary(),
+        "e2e": {"value": world * e / (e2e_ms * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+                "includes": "H2D of x and edge_index from pinned memory, CSR build, fwd, bwd, D2H of loss and 4 param grads"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+
+
+def profile_attention_kernels(conv, x, edge_index, d_out, mode, reps):
+    """Times each attention kernel alone with CUDA events on the stream it is launched on."""
+    from ampnet_b200 import _lib
+    from ampnet_b200 import functional as F_
+    from ampnet_b200.graph import get_graph
+    dev = x.device
+    g = get_graph(edge_index, x.shape[0])
+    mha = conv.multi_head_attention
+    with torch.no_grad():
+        stages = F_.profile_stages(x.detach(), g, mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight,
+                                   mha.out_proj.bias, conv.num_heads, d_out, mode, reps)
+    return stages
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
+    ap.add_argument("--graph", default="uniform", choices=["uniform", "skewed"])
+    ap.add_argument("--mode", default=os.environ.get("AMPNET_B200_BENCH_MODE", "fp32"))
+    ap.add_argument("--cpu-sample-edges", type=int, default=4096)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
