@@ -1,0 +1,402 @@
+// bf16 tensor-core family: fused per-edge multi-head attention + mean aggregation on tcgen05.
+//
+// Replaces the reference's per-edge chain (src/ampnet/conv/amp_conv.py:24-51 ->
+// torch.nn.MultiheadAttention: head split, q*hd^-1/2, bmm, softmax, bmm --
+// src/ampnet/conv/custom_multihead_attn_forward.py:4140-4186, 4376-4387) and PyG's scatter-mean
+// (amp_conv.py:11) with ONE persistent, warp-specialised kernel per direction:
+//
+//   producer warp : dynamic node scheduler + TMA (cp.async.bulk.tensor, 128B swizzle) of the
+//                   destination's Q tile (once per node) and each in-edge's K and V tiles
+//                   ("gather by edge index" = a TMA box at row src*F of the node-major tensors);
+//   MMA warp      : one elected thread issues tcgen05.mma:  S_h = Q_h K_h^T  (SS, K-major operands,
+//                   head = 32-byte slice of the 128-byte swizzled row) into TMEM and
+//                   O_h = P_h V_h (TS: P read from TMEM, V as MN-major operand straight from the
+//                   row-major tile);
+//   2 softmax warpgroups: thread = one destination token (TMEM lane); row max / exp2 / row sum in
+//                   registers, P written back to TMEM as bf16, per-edge normalised O accumulated in
+//                   registers over all in-edges of the destination (the mean aggregation: no
+//                   atomics, no [E,F,d] message tensor, no [E,H,F,F] probabilities in HBM).
+//
+// Layouts: Q', K, V are bf16 [N, F, 64] node-major, rows of 128 bytes; Q' is pre-multiplied by
+// log2(e)/sqrt(hd) so that scores are in the log2 domain.  lse2[p,h,i] = max + log2(sum) per
+// destination-sorted edge slot p is saved for the backward recompute.
+#include <cuda_bf16.h>
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace ampconv {
+namespace {
+
+using namespace umma;
+
+constexpr int kD = 64;                 // embed dim of this kernel family (one 128-byte swizzle atom per row)
+constexpr int kTileBytes = 128 * 128;  // 128 tokens x 64 bf16
+constexpr int kStages = 4;             // K/V ring depth
+constexpr int kFwdThreads = 320;       // 2 softmax warpgroups + producer warp + MMA warp
+
+struct NodeSlot {
+  int node, p_begin, p_end;
+  float inv_deg;
+};
+
+struct FwdSmem {
+  // tiles first (1024-byte aligned), then bookkeeping
+  uint8_t q[2][kTileBytes];
+  uint8_t kv[kStages][2][kTileBytes];
+  uint64_t q_full[2], q_empty[2];
+  uint64_t kv_full[kStages], kv_empty[kStages];
+  uint64_t s_full[2], s_empty[2], p_full[2], p_empty[2];
+  uint64_t o_full[2][2], o_empty[2][2];
+  NodeSlot slot[2];
+  uint32_t tmem_base;
+  float acc[32][256];   // per-thread output accumulators [heads-per-warpgroup * HD][softmax thread]
+};
+
+// first failure wins: status = code | blockIdx << 16
+#define AMP_FAIL(code)                                                       \
+  do {                                                                       \
+    atomicCAS(status, 0, (int)((code) | (blockIdx.x << 16)));                \
+    goto fail;                                                               \
+  } while (0)
+#define AMP_WAIT(bar, parity, code)                         \
+  do {                                                      \
+    if (!mbar_wait((bar), (parity))) AMP_FAIL(code);        \
+  } while (0)
+
+template <int HD>
+__global__ void __launch_bounds__(kFwdThreads, 1)
+attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                     const __grid_constant__ CUtensorMap mapV, const int32_t* __restrict__ rowptr,
+                     const int32_t* __restrict__ dst_src, const float* __restrict__ inv_deg,
+                     const int32_t* __restrict__ order, int* __restrict__ counter, int* __restrict__ status,
+                     float* __restrict__ agg, float* __restrict__ lse2, int N, int F) {
+  constexpr int H = kD / HD;        // heads
+  constexpr int HL = H / 2;         // heads per softmax warpgroup (head h belongs to warpgroup h & 1)
+  static_assert(H % 2 == 0, "this kernel splits heads between two warpgroups");
+  extern __shared__ uint8_t smem_raw[];
+  FwdSmem& sm = *reinterpret_cast<FwdSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 9) tmem_alloc(&sm.tmem_base, 512);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sm.q_full[i], 1);
+      mbar_init(&sm.q_empty[i], 1 + 256);
+      mbar_init(&sm.s_full[i], 1);
+      mbar_init(&sm.s_empty[i], 128);
+      mbar_init(&sm.p_full[i], 128);
+      mbar_init(&sm.p_empty[i], 1);
+      for (int j = 0; j < 2; ++j) {
+        mbar_init(&sm.o_full[i][j], 1);
+        mbar_init(&sm.o_empty[i][j], 128);
+      }
+    }
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&sm.kv_full[i], 1);
+      mbar_init(&sm.kv_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 8 && lane == 0) {
+    prefetch_tensormap(&mapQ);
+    prefetch_tensormap(&mapK);
+    prefetch_tensormap(&mapV);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+  // TMEM columns: S[b] = b*128 (fp32 scores), P[b] = 256 + b*64 (bf16 pairs), O[b][ob] = 384 + (2b+ob)*HD
+  const int nqk = ((F + 15) >> 4) << 4;   // MMA N of the score tile
+  const int ksteps = (F + 15) >> 4;       // K steps of P V
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------ producer / scheduler
+    // The whole warp walks the node list (dynamic scheduler); lane 0 drives the mbarriers and TMA.
+    // Isolated nodes never enter the pipeline: the warp writes their zero rows directly.
+    uint32_t qi = 0, ei = 0;
+    for (;;) {
+      int node = -1, pb = 0, pe = 0;
+      if (lane == 0) {
+        const int idx = atomicAdd(counter, 1);
+        node = idx < N ? (order ? order[idx] : idx) : -1;
+        if (node >= 0) {
+          pb = rowptr[node];
+          pe = rowptr[node + 1];
+        }
+      }
+      node = __shfl_sync(0xffffffffu, node, 0);
+      pb = __shfl_sync(0xffffffffu, pb, 0);
+      pe = __shfl_sync(0xffffffffu, pe, 0);
+      if (node >= 0 && pe == pb) {
+        float4* z = reinterpret_cast<float4*>(agg + (int64_t)node * F * kD);
+        for (int i = lane; i < F * (kD / 4); i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        continue;
+      }
+      int failed = 0;
+      if (lane == 0) {
+        const uint32_t qb = qi & 1;
+        if (!mbar_wait(&sm.q_empty[qb], ((qi >> 1) & 1) ^ 1)) {
+          failed = 101;
+        } else {
+          NodeSlot ns;
+          ns.node = node;
+          ns.p_begin = pb;
+          ns.p_end = pe;
+          ns.inv_deg = node >= 0 ? inv_deg[node] : 0.f;
+          sm.slot[qb] = ns;
+          if (node < 0) {
+            mbar_arrive(&sm.q_full[qb]);
+          } else {
+            mbar_arrive_expect_tx(&sm.q_full[qb], kTileBytes);
+            tma_load_3d(sm.q[qb], &mapQ, &sm.q_full[qb], 0, 0, node);
+            int src_next = dst_src[pb];
+            for (int p = pb; p < pe; ++p, ++ei) {
+              const int src = src_next;
+              if (p + 1 < pe) src_next = dst_src[p + 1];
+              const uint32_t st = ei % kStages;
+              if (!mbar_wait(&sm.kv_empty[st], ((ei / kStages) & 1) ^ 1)) {
+                failed = 102;
+                break;
+              }
+              mbar_arrive_expect_tx(&sm.kv_full[st], 2 * kTileBytes);
+              tma_load_3d(sm.kv[st][0], &mapK, &sm.kv_full[st], 0, 0, src);
+              tma_load_3d(sm.kv[st][1], &mapV, &sm.kv_full[st], 0, 0, src);
+            }
+          }
+          ++qi;
+        }
+      }
+      failed = __shfl_sync(0xffffffffu, failed, 0);
+      if (failed) AMP_FAIL(failed);
+      if (node < 0) break;
+    }
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_qk = idesc_bf16(128, nqk, 0, 0);
+      const uint32_t idesc_pv = idesc_bf16(128, HD, 0, 1);
+      uint32_t qi = 0, ei = 0, c[2] = {0, 0};
+      bool have_prev = false;
+      uint32_t pv_b = 0, pv_st = 0, pv_h = 0, pv_c = 0;
+      bool pv_last = false;
+      auto issue_pv = [&]() -> bool {
+        if (!mbar_wait(&sm.p_full[pv_b], pv_c & 1)) return false;
+        const uint32_t ob = pv_c & 1;
+        if (!mbar_wait(&sm.o_empty[pv_b][ob], ((pv_c >> 1) & 1) ^ 1)) return false;
+        tc_fence_after();
+        const uint32_t v_base = smem_u32(sm.kv[pv_st][1]) + pv_h * (HD * 2);
+        const uint32_t o_col = tmem + 384 + (2 * pv_b + ob) * HD;
+        const uint32_t p_col = tmem + 256 + pv_b * 64;
+        for (int ks = 0; ks < ksteps; ++ks)
+          mma_ts(o_col, p_col + 8 * ks, smem_desc(v_base + ks * 2048, 16, 1024, LAYOUT_SW128), idesc_pv, ks > 0);
+        mma_commit(&sm.o_full[pv_b][ob]);
+        mma_commit(&sm.p_empty[pv_b]);
+        if (pv_last) mma_commit(&sm.kv_empty[pv_st]);
+        return true;
+      };
+      for (;;) {
+        const uint32_t qb = qi & 1;
+        AMP_WAIT(&sm.q_full[qb], (qi >> 1) & 1, 201);
+        const NodeSlot ns = sm.slot[qb];
+        if (ns.node < 0) break;
+        if (ns.p_end == ns.p_begin) mbar_arrive(&sm.q_empty[qb]);
+        for (int p = ns.p_begin; p < ns.p_end; ++p, ++ei) {
+          const uint32_t st = ei % kStages;
+          AMP_WAIT(&sm.kv_full[st], (ei / kStages) & 1, 202);
+#pragma unroll
+          for (int h = 0; h < H; ++h) {
+            const uint32_t b = h & 1;
+            AMP_WAIT(&sm.s_empty[b], (c[b] & 1) ^ 1, 203);
+            tc_fence_after();
+            const uint32_t qa = smem_u32(sm.q[qb]) + h * (HD * 2);
+            const uint32_t ka = smem_u32(sm.kv[st][0]) + h * (HD * 2);
+#pragma unroll
+            for (int ks = 0; ks < HD / 16; ++ks)
+              mma_ss(tmem + b * 128, smem_desc(qa + ks * 32, 16, 1024, LAYOUT_SW128),
+                     smem_desc(ka + ks * 32, 16, 1024, LAYOUT_SW128), idesc_qk, ks > 0);
+            mma_commit(&sm.s_full[b]);
+            if (p + 1 == ns.p_end && h == H - 1) mma_commit(&sm.q_empty[qb]);
+            if (have_prev && !issue_pv()) AMP_FAIL(204);
+            pv_b = b; pv_st = st; pv_h = h; pv_c = c[b]; pv_last = (h == H - 1);
+            have_prev = true;
+            ++c[b];
+          }
+        }
+        ++qi;
+      }
+      if (have_prev && !issue_pv()) AMP_FAIL(205);
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warpgroups
+    const uint32_t b = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const bool row_ok = row < F;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t qi = 0, c = 0;
+    float* acc = &sm.acc[0][b * 128 + row];   // element x of this thread: acc[x * 256]
+    for (;;) {
+      const uint32_t qb = qi & 1;
+      AMP_WAIT(&sm.q_full[qb], (qi >> 1) & 1, 301);
+      const NodeSlot ns = sm.slot[qb];
+      mbar_arrive(&sm.q_empty[qb]);   // slot contents are now in registers (256 of the 257 arrivals)
+      if (ns.node < 0) break;
+#pragma unroll
+      for (int x = 0; x < HL * HD; ++x) acc[x * 256] = 0.f;
+      float l_prev = 1.f;
+      uint32_t t = 0;
+      // adds O / l of this warpgroup's item `cc` into the accumulators of local head hl_prev
+      auto consume = [&](uint32_t cc, int hl_prev, float l) -> bool {
+        const uint32_t ob = cc & 1;
+        if (!mbar_wait(&sm.o_full[b][ob], (cc >> 1) & 1)) return false;
+        tc_fence_after();
+        uint32_t o[HD];
+        if constexpr (HD == 16) {
+          tmem_ld_32x32b_x16(lane_base + 384 + (2 * b + ob) * HD, o);
+        } else {
+          tmem_ld_32x32b_x32(lane_base + 384 + (2 * b + ob) * HD, o);
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&sm.o_empty[b][ob]);
+        const float inv_l = 1.0f / l;
+        float* a = acc + hl_prev * HD * 256;
+#pragma unroll
+        for (int x = 0; x < HD; ++x) a[x * 256] = fmaf(__uint_as_float(o[x]), inv_l, a[x * 256]);
+        return true;
+      };
+      for (int p = ns.p_begin; p < ns.p_end; ++p) {
+#pragma unroll
+        for (int hl = 0; hl < HL; ++hl) {
+          const int h = 2 * hl + b;
+          AMP_WAIT(&sm.s_full[b], c & 1, 302);
+          tc_fence_after();
+          uint32_t s[128];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tmem_ld_32x32b_x32(lane_base + b * 128 + 32 * k, *reinterpret_cast<uint32_t(*)[32]>(&s[32 * k]));
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(&sm.s_empty[b]);
+          // mask source tokens >= F (their K rows are TMA zero fill, the score columns may be stale)
+          if (F < 128) {
+#pragma unroll
+            for (int j = 0; j < 128; ++j)
+              if (j >= F) s[j] = __float_as_uint(-CUDART_INF_F);
+          }
+          float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F;
+#pragma unroll
+          for (int j = 0; j < 128; j += 2) {
+            m0 = fmaxf(m0, __uint_as_float(s[j]));
+            m1 = fmaxf(m1, __uint_as_float(s[j + 1]));
+          }
+          const float m = fmaxf(m0, m1);
+          AMP_WAIT(&sm.p_empty[b], (c & 1) ^ 1, 303);
+          tc_fence_after();
+          float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float e0 = ex2_approx(__uint_as_float(s[32 * k + 2 * j]) - m);
+              const float e1 = ex2_approx(__uint_as_float(s[32 * k + 2 * j + 1]) - m);
+              l0 += e0;
+              l1 += e1;
+              pk[j] = pack_bf16x2(e0, e1);
+            }
+            tmem_st_32x32b_x16(lane_base + 256 + b * 64 + 16 * k, pk);
+          }
+          const float l = l0 + l1;
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&sm.p_full[b]);
+          if (row_ok) lse2[((int64_t)p * H + h) * F + row] = m + __log2f(l);
+          if (t > 0) {
+            if (!consume(c - 1, (hl + HL - 1) % HL, l_prev)) AMP_FAIL(304);
+          }
+          l_prev = l;
+          ++c;
+          ++t;
+        }
+      }
+      if (t > 0) {
+        if (!consume(c - 1, HL - 1, l_prev)) AMP_FAIL(305);
+      }
+      if (row_ok) {
+        float* o = agg + ((int64_t)ns.node * F + row) * kD;
+#pragma unroll
+        for (int hl = 0; hl < HL; ++hl) {
+          float4* o4 = reinterpret_cast<float4*>(o + (2 * hl + b) * HD);
+          const float* a = acc + hl * HD * 256;
+#pragma unroll
+          for (int x = 0; x < HD; x += 4)
+            o4[x >> 2] = make_float4(a[x * 256] * ns.inv_deg, a[(x + 1) * 256] * ns.inv_deg,
+                                     a[(x + 2) * 256] * ns.inv_deg, a[(x + 3) * 256] * ns.inv_deg);
+        }
+      }
+      ++qi;
+    }
+  }
+fail:
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+}  // namespace ampconv
+
+using namespace ampconv;
+
+extern "C" int ampconv_attn_bf16_supported(int F, int d, int H) {
+  if (d != kD || H <= 0 || d % H) return 0;
+  const int hd = d / H;
+  return (hd == 16 || hd == 32) && F >= 1 && F <= 128;
+}
+
+extern "C" int ampconv_attn_fwd_bf16(const void* q, const void* k, const void* v,
+                                     const int32_t* dst_rowptr, const int32_t* dst_src, const float* inv_deg,
+                                     const int32_t* order, float* agg, float* lse2,
+                                     int64_t N, int64_t E, int F, int d, int H,
+                                     void* workspace, size_t workspace_bytes, void* stream_) {
+  AMPCONV_REQUIRE(N >= 0 && E >= 0 && F > 0 && d > 0 && H > 0 && d % H == 0);
+  if (!ampconv_attn_bf16_supported(F, d, H)) return AMPCONV_ERR_UNSUPPORTED;
+  if (N == 0) return AMPCONV_OK;
+  AMPCONV_REQUIRE(q && k && v && dst_rowptr && inv_deg && agg && workspace && (E == 0 || (dst_src && lse2)));
+  if (workspace_bytes < 256) return AMPCONV_ERR_WORKSPACE;
+  cudaStream_t stream = as_stream(stream_);
+  CUtensorMap mq, mk, mv;
+  if (!make_tensor_map_bf16_3d(&mq, q, kD, F, N, kD, 128) || !make_tensor_map_bf16_3d(&mk, k, kD, F, N, kD, 128) ||
+      !make_tensor_map_bf16_3d(&mv, v, kD, F, N, kD, 128))
+    return AMPCONV_ERR_CUDA;
+  int* counter = reinterpret_cast<int*>(workspace);
+  int* status = counter + 1;
+  AMPCONV_CUDA_TRY(cudaMemsetAsync(counter, 0, 2 * sizeof(int), stream));
+  const size_t smem = sizeof(FwdSmem) + 1024;
+  const int grid = (int)(N < sm_count() ? N : sm_count());
+  const int hd = d / H;
+  if (hd == 16) {
+    AMPCONV_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_bf16_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_fwd_bf16_kernel<16><<<grid, kFwdThreads, smem, stream>>>(mq, mk, mv, dst_rowptr, dst_src, inv_deg, order, counter,
+                                                                  status, agg, lse2, (int)N, F);
+  } else {
+    AMPCONV_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_bf16_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_fwd_bf16_kernel<32><<<grid, kFwdThreads, smem, stream>>>(mq, mk, mv, dst_rowptr, dst_src, inv_deg, order, counter,
+                                                                  status, agg, lse2, (int)N, F);
+  }
+  AMPCONV_CHECK_LAUNCH();
+  return AMPCONV_OK;
+}
+
+// Reads back the protocol status word written by the bf16 kernels (0 = ok).  Synchronises the stream.
+extern "C" int ampconv_bf16_status(const void* workspace, int* status_host, void* stream_) {
+  AMPCONV_REQUIRE(workspace && status_host);
+  cudaStream_t stream = as_stream(stream_);
+  AMPCONV_CUDA_TRY(cudaMemcpyAsync(status_host, reinterpret_cast<const int*>(workspace) + 1, sizeof(int),
+                                   cudaMemcpyDeviceToHost, stream));
+  AMPCONV_CUDA_TRY(cudaStreamSynchronize(stream));
+  return AMPCONV_OK;
+}

@@ -1,0 +1,472 @@
+// bf16 tensor-core family, backward: flash-style recompute of the per-edge attention from the saved
+// log-sum-exp (autograd of custom_multihead_attn_forward.py:4140-4186 + PyG scatter-mean, which the
+// reference gets from saved [E,H,F,F] probabilities).  Two persistent warp-specialised kernels built
+// from one template; both accumulate over a node's edges on chip (no atomics, deterministic):
+//
+//   MODE_DQ  (destination-sorted): own tiles = Q'_t, dO_t (per destination), edge tiles = K_s, V_s.
+//       X = Q_h K_h^T, Y = dO_h V_h^T;  P = exp2(X - lse2_i), W = P o Y, delta_i = sum_j W_ij;
+//       TX = P K_h, TY = W K_h (A from TMEM, B = K tile as MN-major operand);
+//       dQ_h += TY - delta o TX.                      delta[p,h,i] is written for MODE_DKV.
+//   MODE_DKV (source-sorted): own tiles = K_s, V_s (per source), edge tiles = Q'_t, dO_t plus the
+//       lse2 / delta rows of the edge (bulk copies).  Everything is transposed (thread = source token):
+//       X = K_h Q_h^T, Y = V_h dO_h^T;  P^T = exp2(X - lse2_col), dS^T = P^T o (Y - delta_col);
+//       TX = P^T dO_h -> dV_h,  TY = dS^T Q'_h -> dK_h.
+//
+// TMEM: warpgroup b owns columns [256b, 256b+256): X at +0, Y at +128; the bf16 operands P / W (or
+// P^T / dS^T) overwrite columns +0..63 of X / Y in place; TX / TY land in columns +64.. of X / Y.
+#include <cuda_bf16.h>
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace ampconv {
+namespace {
+
+using namespace umma;
+
+constexpr int kD = 64;
+constexpr int kTileBytes = 128 * 128;
+constexpr int kThreads = 320;
+constexpr int MODE_DQ = 0, MODE_DKV = 1;
+constexpr int kStatFloats = 4 * 128;   // H * roundup4(F) <= 512 floats per edge and statistic
+
+struct NodeSlot {
+  int node, e_begin, e_end;
+};
+
+template <int MODE>
+struct BwdSmem {
+  static constexpr int NS = MODE == MODE_DQ ? 3 : 2;
+  static constexpr int NACC = MODE == MODE_DQ ? 1 : 2;
+  uint8_t own[2][2][kTileBytes];        // [slot][tile 0/1]
+  uint8_t edge[NS][2][kTileBytes];      // [stage][tile 0/1]
+  float stat[NS][2][kStatFloats];       // MODE_DKV: lse2 / delta rows of the edge
+  float acc[NACC * 32][256];
+  uint64_t own_full[2], own_empty[2];
+  uint64_t edge_full[NS], edge_empty[NS];
+  uint64_t xy_full[2], xy_empty[2], u_full[2], t_full[2];
+  NodeSlot slot[2];
+  uint32_t tmem_base;
+};
+
+#define AMP_FAIL(code)                                                       \
+  do {                                                                       \
+    atomicCAS(status, 0, (int)((code) | (blockIdx.x << 16)));                \
+    goto fail;                                                               \
+  } while (0)
+#define AMP_WAIT(bar, parity, code)                         \
+  do {                                                      \
+    if (!mbar_wait((bar), (parity))) AMP_FAIL(code);        \
+  } while (0)
+
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// own0/own1: tensor maps of the per-node tiles, oth0/oth1: of the per-edge tiles.
+// rowptr/nbr: CSR of the pass (by destination for MODE_DQ, by source for MODE_DKV); slot_of[e] = position of
+// edge e in the statistics arrays (NULL: identity).  d_qkv: fp32 [rows, 192].
+template <int HD, int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_constant__ CUtensorMap own1,
+                     const __grid_constant__ CUtensorMap oth0, const __grid_constant__ CUtensorMap oth1,
+                     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr,
+                     const int32_t* __restrict__ slot_of, const float* __restrict__ lse2, float* __restrict__ delta,
+                     float* __restrict__ d_qkv, int* __restrict__ counter, int* __restrict__ status,
+                     int N, int F, float out_scale0, float out_scale1) {
+  using Smem = BwdSmem<MODE>;
+  constexpr int NS = Smem::NS;
+  constexpr int H = kD / HD, HL = H / 2;
+  static_assert(H % 2 == 0, "heads are split between two warpgroups");
+  extern __shared__ uint8_t smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Fs = (F + 3) & ~3;   // row stride of the statistics arrays
+
+  if (warp == 9) tmem_alloc(&sm.tmem_base, 512);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sm.own_full[i], 1);
+      mbar_init(&sm.own_empty[i], 1 + 256);
+      mbar_init(&sm.xy_full[i], 1);
+      mbar_init(&sm.xy_empty[i], 128);
+      mbar_init(&sm.u_full[i], 128);
+      mbar_init(&sm.t_full[i], 1);
+    }
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&sm.edge_full[i], 1);
+      mbar_init(&sm.edge_empty[i], MODE == MODE_DKV ? 1 + 256 : 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 8 && lane == 0) {
+    prefetch_tensormap(&own0);
+    prefetch_tensormap(&own1);
+    prefetch_tensormap(&oth0);
+    prefetch_tensormap(&oth1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+  const int nqk = ((F + 15) >> 4) << 4;
+  const int ksteps = (F + 15) >> 4;
+  const uint32_t stat_bytes = (uint32_t)(H * Fs * sizeof(float));
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------ producer / scheduler
+    uint32_t qi = 0, ei = 0;
+    for (;;) {
+      int node = -1, eb = 0, ee = 0;
+      if (lane == 0) {
+        const int idx = atomicAdd(counter, 1);
+        node = idx < N ? idx : -1;
+        if (node >= 0) {
+          eb = rowptr[node];
+          ee = rowptr[node + 1];
+        }
+      }
+      node = __shfl_sync(0xffffffffu, node, 0);
+      eb = __shfl_sync(0xffffffffu, eb, 0);
+      ee = __shfl_sync(0xffffffffu, ee, 0);
+      if (node >= 0 && ee == eb) {
+        // node without edges in this pass: its gradient rows are zero
+        const int ncol = MODE == MODE_DQ ? kD : 2 * kD;
+        const int col0 = MODE == MODE_DQ ? 0 : kD;
+        for (int i = lane; i < F * (ncol / 4); i += 32) {
+          const int r = i / (ncol / 4), c4 = i - r * (ncol / 4);
+          *reinterpret_cast<float4*>(d_qkv + ((int64_t)node * F + r) * (3 * kD) + col0 + 4 * c4) =
+              make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        continue;
+      }
+      int failed = 0;
+      if (lane == 0) {
+        const uint32_t qb = qi & 1;
+        if (!mbar_wait(&sm.own_empty[qb], ((qi >> 1) & 1) ^ 1)) {
+          failed = 101;
+        } else {
+          NodeSlot ns;
+          ns.node = node;
+          ns.e_begin = eb;
+          ns.e_end = ee;
+          sm.slot[qb] = ns;
+          if (node < 0) {
+            mbar_arrive(&sm.own_full[qb]);
+          } else {
+            mbar_arrive_expect_tx(&sm.own_full[qb], 2 * kTileBytes);
+            tma_load_3d(sm.own[qb][0], &own0, &sm.own_full[qb], 0, 0, node);
+            tma_load_3d(sm.own[qb][1], &own1, &sm.own_full[qb], 0, 0, node);
+            int nb_next = nbr[eb];
+            for (int e = eb; e < ee; ++e, ++ei) {
+              const int nb = nb_next;
+              if (e + 1 < ee) nb_next = nbr[e + 1];
+              const uint32_t st = ei % NS;
+              if (!mbar_wait(&sm.edge_empty[st], ((ei / NS) & 1) ^ 1)) {
+                failed = 102;
+                break;
+              }
+              if (MODE == MODE_DKV) {
+                const int64_t sl = slot_of ? slot_of[e] : e;
+                mbar_arrive_expect_tx(&sm.edge_full[st], 2 * kTileBytes + 2 * stat_bytes);
+                bulk_load(sm.stat[st][0], lse2 + sl * H * Fs, stat_bytes, &sm.edge_full[st]);
+                bulk_load(sm.stat[st][1], delta + sl * H * Fs, stat_bytes, &sm.edge_full[st]);
+              } else {
+                mbar_arrive_expect_tx(&sm.edge_full[st], 2 * kTileBytes);
+              }
+              tma_load_3d(sm.edge[st][0], &oth0, &sm.edge_full[st], 0, 0, nb);
+              tma_load_3d(sm.edge[st][1], &oth1, &sm.edge_full[st], 0, 0, nb);
+            }
+          }
+          ++qi;
+        }
+      }
+      failed = __shfl_sync(0xffffffffu, failed, 0);
+      if (failed) AMP_FAIL(failed);
+      if (node < 0) break;
+    }
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_xy = idesc_bf16(128, nqk, 0, 0);
+      const uint32_t idesc_t = idesc_bf16(128, HD, 0, 1);
+      uint32_t qi = 0, ei = 0, c[2] = {0, 0};
+      bool have_prev = false;
+      uint32_t t_b = 0, t_st = 0, t_h = 0, t_c = 0;
+      bool t_last = false;
+      // T MMAs of the previously issued item: TX = X' * B_tx, TY = Y' * B_ty (B operands MN-major)
+      auto issue_t = [&]() -> bool {
+        if (!mbar_wait(&sm.u_full[t_b], t_c & 1)) return false;
+        tc_fence_after();
+        const uint32_t x_col = tmem + t_b * 256, y_col = x_col + 128;
+        const uint32_t btx = smem_u32(sm.edge[t_st][MODE == MODE_DQ ? 0 : 1]) + t_h * (HD * 2);
+        const uint32_t bty = smem_u32(sm.edge[t_st][0]) + t_h * (HD * 2);
+        for (int ks = 0; ks < ksteps; ++ks)
+          mma_ts(x_col + 64, x_col + 8 * ks, smem_desc(btx + ks * 2048, 16, 1024, LAYOUT_SW128), idesc_t, ks > 0);
+        for (int ks = 0; ks < ksteps; ++ks)
+          mma_ts(y_col + 64, y_col + 8 * ks, smem_desc(bty + ks * 2048, 16, 1024, LAYOUT_SW128), idesc_t, ks > 0);
+        mma_commit(&sm.t_full[t_b]);
+        if (t_last) mma_commit(&sm.edge_empty[t_st]);
+        return true;
+      };
+      for (;;) {
+        const uint32_t qb = qi & 1;
+        AMP_WAIT(&sm.own_full[qb], (qi >> 1) & 1, 201);
+        const NodeSlot ns = sm.slot[qb];
+        if (ns.node < 0) break;
+        for (int e = ns.e_begin; e < ns.e_end; ++e, ++ei) {
+          const uint32_t st = ei % NS;
+          AMP_WAIT(&sm.edge_full[st], (ei / NS) & 1, 202);
+#pragma unroll
+          for (int h = 0; h < H; ++h) {
+            const uint32_t b = h & 1;
+            AMP_WAIT(&sm.xy_empty[b], (c[b] & 1) ^ 1, 203);
+            tc_fence_after();
+            const uint32_t hb = h * (HD * 2);
+            const uint32_t a0 = smem_u32(sm.own[qb][0]) + hb, a1 = smem_u32(sm.own[qb][1]) + hb;
+            const uint32_t b0 = smem_u32(sm.edge[st][0]) + hb, b1 = smem_u32(sm.edge[st][1]) + hb;
+#pragma unroll
+            for (int ks = 0; ks < HD / 16; ++ks)
+              mma_ss(tmem + b * 256, smem_desc(a0 + ks * 32, 16, 1024, LAYOUT_SW128),
+                     smem_desc(b0 + ks * 32, 16, 1024, LAYOUT_SW128), idesc_xy, ks > 0);
+#pragma unroll
+            for (int ks = 0; ks < HD / 16; ++ks)
+              mma_ss(tmem + b * 256 + 128, smem_desc(a1 + ks * 32, 16, 1024, LAYOUT_SW128),
+                     smem_desc(b1 + ks * 32, 16, 1024, LAYOUT_SW128), idesc_xy, ks > 0);
+            mma_commit(&sm.xy_full[b]);
+            if (e + 1 == ns.e_end && h == H - 1) mma_commit(&sm.own_empty[qb]);
+            if (have_prev && !issue_t()) AMP_FAIL(204);
+            t_b = b; t_st = st; t_h = h; t_c = c[b]; t_last = (h == H - 1);
+            have_prev = true;
+            ++c[b];
+          }
+        }
+        ++qi;
+      }
+      if (have_prev && !issue_t()) AMP_FAIL(205);
+    }
+  } else {
+    // ------------------------------------------------------------------ elementwise warpgroups
+    const uint32_t b = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const bool row_ok = row < F;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + b * 256;
+    uint32_t qi = 0, c = 0, ei = 0;
+    float* acc = &sm.acc[0][b * 128 + row];
+    for (;;) {
+      const uint32_t qb = qi & 1;
+      AMP_WAIT(&sm.own_full[qb], (qi >> 1) & 1, 301);
+      const NodeSlot ns = sm.slot[qb];
+      mbar_arrive(&sm.own_empty[qb]);
+      if (ns.node < 0) break;
+#pragma unroll
+      for (int x = 0; x < Smem::NACC * HL * HD; ++x) acc[x * 256] = 0.f;
+      float dl_prev = 0.f;
+      uint32_t t = 0;
+      // folds TX / TY of this warpgroup's item into the accumulators of local head hl_prev and frees X / Y
+      auto readback = [&](uint32_t cc, int hl_prev, float dl) -> bool {
+        if (!mbar_wait(&sm.t_full[b], cc & 1)) return false;
+        tc_fence_after();
+        uint32_t tx[HD], ty[HD];
+        if constexpr (HD == 16) {
+          tmem_ld_32x32b_x16(lane_base + 64, tx);
+          tmem_ld_32x32b_x16(lane_base + 128 + 64, ty);
+        } else {
+          tmem_ld_32x32b_x32(lane_base + 64, tx);
+          tmem_ld_32x32b_x32(lane_base + 128 + 64, ty);
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&sm.xy_empty[b]);
+        float* a = acc + hl_prev * HD * 256;
+        if (MODE == MODE_DQ) {
+#pragma unroll
+          for (int x = 0; x < HD; ++x)
+            a[x * 256] += __uint_as_float(ty[x]) - dl * __uint_as_float(tx[x]);
+        } else {
+          float* a2 = a + HL * HD * 256;
+#pragma unroll
+          for (int x = 0; x < HD; ++x) {
+            a[x * 256] += __uint_as_float(ty[x]);    // dK
+            a2[x * 256] += __uint_as_float(tx[x]);   // dV
+          }
+        }
+        return true;
+      };
+      for (int e = ns.e_begin; e < ns.e_end; ++e, ++ei) {
+        const uint32_t st = ei % NS;
+        const int64_t sl = (MODE == MODE_DQ) ? (int64_t)e : 0;
+#pragma unroll
+        for (int hl = 0; hl < HL; ++hl) {
+          const int h = 2 * hl + b;
+          // the previous item of this warpgroup must leave X / Y before the MMA warp can refill them
+          if (t > 0) {
+            if (!readback(c - 1, (hl + HL - 1) % HL, dl_prev)) AMP_FAIL(304);
+          }
+          float L = 0.f;
+          if (MODE == MODE_DQ) L = row_ok ? lse2[(sl * H + h) * Fs + row] : 0.f;
+          AMP_WAIT(&sm.xy_full[b], c & 1, 302);
+          tc_fence_after();
+          const float* Ls = sm.stat[st][0] + h * Fs;
+          const float* Ds = sm.stat[st][1] + h * Fs;
+          float dl0 = 0.f, dl1 = 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (32 * k < nqk) {
+              uint32_t xs[32], ys[32];
+              tmem_ld_32x32b_x32(lane_base + 32 * k, xs);
+              tmem_ld_32x32b_x32(lane_base + 128 + 32 * k, ys);
+              tmem_ld_wait();
+              uint32_t px[16], py[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int c0 = 32 * k + 2 * j;
+                float p0, p1, u0, u1;
+                if (MODE == MODE_DQ) {
+                  p0 = ex2_approx(__uint_as_float(xs[2 * j]) - L);
+                  p1 = ex2_approx(__uint_as_float(xs[2 * j + 1]) - L);
+                  u0 = p0 * __uint_as_float(ys[2 * j]);
+                  u1 = p1 * __uint_as_float(ys[2 * j + 1]);
+                } else {
+                  const float2 l2 = *reinterpret_cast<const float2*>(Ls + c0);
+                  const float2 d2 = *reinterpret_cast<const float2*>(Ds + c0);
+                  p0 = ex2_approx(__uint_as_float(xs[2 * j]) - l2.x);
+                  p1 = ex2_approx(__uint_as_float(xs[2 * j + 1]) - l2.y);
+                  u0 = p0 * (__uint_as_float(ys[2 * j]) - d2.x);
+                  u1 = p1 * (__uint_as_float(ys[2 * j + 1]) - d2.y);
+                }
+                if (F < 128) {
+                  if (c0 >= F) { p0 = 0.f; u0 = 0.f; }
+                  if (c0 + 1 >= F) { p1 = 0.f; u1 = 0.f; }
+                }
+                dl0 += u0;
+                dl1 += u1;
+                px[j] = pack_bf16x2(p0, p1);
+                py[j] = pack_bf16x2(u0, u1);
+              }
+              tmem_st_32x32b_x16(lane_base + 16 * k, px);
+              tmem_st_32x32b_x16(lane_base + 128 + 16 * k, py);
+            }
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&sm.u_full[b]);
+          const float dl = dl0 + dl1;
+          if (MODE == MODE_DQ) {
+            if (row_ok) delta[(sl * H + h) * Fs + row] = dl;
+          } else if (hl == HL - 1) {
+            mbar_arrive(&sm.edge_empty[st]);   // statistics rows of this stage are no longer needed by this thread
+          }
+          dl_prev = dl;
+          ++c;
+          ++t;
+        }
+      }
+      if (t > 0) {
+        if (!readback(c - 1, HL - 1, dl_prev)) AMP_FAIL(305);
+      }
+      if (row_ok) {
+        float* o = d_qkv + ((int64_t)ns.node * F + row) * (3 * kD);
+#pragma unroll
+        for (int hl = 0; hl < HL; ++hl) {
+          const float* a = acc + hl * HD * 256;
+          float4* o0 = reinterpret_cast<float4*>(o + (MODE == MODE_DQ ? 0 : kD) + (2 * hl + b) * HD);
+#pragma unroll
+          for (int x = 0; x < HD; x += 4)
+            o0[x >> 2] = make_float4(a[x * 256] * out_scale0, a[(x + 1) * 256] * out_scale0,
+                                     a[(x + 2) * 256] * out_scale0, a[(x + 3) * 256] * out_scale0);
+          if (MODE == MODE_DKV) {
+            const float* a2 = a + HL * HD * 256;
+            float4* o1 = reinterpret_cast<float4*>(o + 2 * kD + (2 * hl + b) * HD);
+#pragma unroll
+            for (int x = 0; x < HD; x += 4)
+              o1[x >> 2] = make_float4(a2[x * 256] * out_scale1, a2[(x + 1) * 256] * out_scale1,
+                                       a2[(x + 2) * 256] * out_scale1, a2[(x + 3) * 256] * out_scale1);
+          }
+        }
+      }
+      ++qi;
+    }
+  }
+fail:
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem, 512);
+}
+
+template <int HD, int MODE>
+int launch_bwd(const CUtensorMap& own0, const CUtensorMap& own1, const CUtensorMap& oth0, const CUtensorMap& oth1,
+               const int32_t* rowptr, const int32_t* nbr, const int32_t* slot_of, const float* lse2, float* delta,
+               float* d_qkv, int* counter, int* status, int N, int F, float s0, float s1, cudaStream_t stream) {
+  const size_t smem = sizeof(BwdSmem<MODE>) + 1024;
+  AMPCONV_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_bf16_kernel<HD, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = N < sm_count() ? N : sm_count();
+  attn_bwd_bf16_kernel<HD, MODE><<<grid, kThreads, smem, stream>>>(own0, own1, oth0, oth1, rowptr, nbr, slot_of, lse2, delta,
+                                                                  d_qkv, counter, status, N, F, s0, s1);
+  AMPCONV_CHECK_LAUNCH();
+  return AMPCONV_OK;
+}
+
+}  // namespace
+}  // namespace ampconv
+
+using namespace ampconv;
+
+extern "C" int ampconv_attn_bf16_supported(int F, int d, int H);
+
+static int bwd_common(int mode, const void* q, const void* k, const void* v, const void* d_agg_bf16,
+                      const int32_t* rowptr, const int32_t* nbr, const int32_t* slot_of, const float* lse2, float* delta,
+                      float* d_qkv, int64_t N, int64_t E, int F, int d, int H, void* workspace, size_t workspace_bytes,
+                      void* stream_) {
+  AMPCONV_REQUIRE(N >= 0 && E >= 0 && F > 0 && d > 0 && H > 0 && d % H == 0);
+  if (!ampconv_attn_bf16_supported(F, d, H)) return AMPCONV_ERR_UNSUPPORTED;
+  if (N == 0) return AMPCONV_OK;
+  AMPCONV_REQUIRE(q && k && v && d_agg_bf16 && rowptr && d_qkv && workspace);
+  AMPCONV_REQUIRE(E == 0 || (nbr && lse2 && delta));
+  if (workspace_bytes < 256) return AMPCONV_ERR_WORKSPACE;
+  cudaStream_t stream = as_stream(stream_);
+  CUtensorMap mq, mk, mv, mg;
+  if (!make_tensor_map_bf16_3d(&mq, q, kD, F, N, kD, 128) || !make_tensor_map_bf16_3d(&mk, k, kD, F, N, kD, 128) ||
+      !make_tensor_map_bf16_3d(&mv, v, kD, F, N, kD, 128) || !make_tensor_map_bf16_3d(&mg, d_agg_bf16, kD, F, N, kD, 128))
+    return AMPCONV_ERR_CUDA;
+  int* counter = reinterpret_cast<int*>(workspace) + (mode == MODE_DQ ? 2 : 4);
+  int* status = reinterpret_cast<int*>(workspace) + 1;
+  AMPCONV_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(int), stream));
+  const int hd = d / H;
+  const float inv_sqrt_hd = 1.0f / sqrtf((float)hd);
+  const float ln2 = 0.6931471805599453f;
+  if (mode == MODE_DQ) {
+    // dQ = hd^-1/2 * (dS K)
+    if (hd == 16)
+      return launch_bwd<16, MODE_DQ>(mq, mg, mk, mv, rowptr, nbr, slot_of, lse2, delta, d_qkv, counter, status, (int)N, F,
+                                    inv_sqrt_hd, 0.f, stream);
+    return launch_bwd<32, MODE_DQ>(mq, mg, mk, mv, rowptr, nbr, slot_of, lse2, delta, d_qkv, counter, status, (int)N, F,
+                                  inv_sqrt_hd, 0.f, stream);
+  }
+  // dK = hd^-1/2 * dS^T Q = ln2 * dS^T Q'  (Q' = Q * log2e / sqrt(hd)),  dV = P^T dO
+  if (hd == 16)
+    return launch_bwd<16, MODE_DKV>(mk, mv, mq, mg, rowptr, nbr, slot_of, lse2, delta, d_qkv, counter, status, (int)N, F, ln2,
+                                   1.f, stream);
+  return launch_bwd<32, MODE_DKV>(mk, mv, mq, mg, rowptr, nbr, slot_of, lse2, delta, d_qkv, counter, status, (int)N, F, ln2,
+                                 1.f, stream);
+}
+
+extern "C" int ampconv_attn_bwd_dq_bf16(const void* q, const void* k, const void* v, const void* d_agg_bf16,
+                                        const float* lse2, const int32_t* dst_rowptr, const int32_t* dst_src,
+                                        float* d_qkv, float* delta, int64_t N, int64_t E, int F, int d, int H,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+  return bwd_common(MODE_DQ, q, k, v, d_agg_bf16, dst_rowptr, dst_src, nullptr, lse2, delta, d_qkv, N, E, F, d, H,
+                    workspace, workspace_bytes, stream);
+}
+
+extern "C" int ampconv_attn_bwd_dkv_bf16(const void* q, const void* k, const void* v, const void* d_agg_bf16,
+                                         const float* lse2, const float* delta, const int32_t* src_rowptr,
+                                         const int32_t* src_dst, const int32_t* src_pos, float* d_qkv,
+                                         int64_t N, int64_t E, int F, int d, int H,
+                                         void* workspace, size_t workspace_bytes, void* stream) {
+  return bwd_common(MODE_DKV, q, k, v, d_agg_bf16, src_rowptr, src_dst, src_pos, lse2, const_cast<float*>(delta), d_qkv,
+                    N, E, F, d, H, workspace, workspace_bytes, stream);
+}

@@ -2,6 +2,8 @@
 // Replaces the aten::mm / addmm calls of F.multi_head_attention_forward
 // (reference era copy src/ampnet/conv/custom_multihead_attn_forward.py:4031-4084, 4436-4437),
 // executed once per node token instead of once per edge token.
+#include <cuda_bf16.h>
+
 #include "gemm_f32.cuh"
 
 namespace ampconv {
@@ -82,7 +84,14 @@ gemm_f32_kernel(const float* __restrict__ A, int64_t sam, int64_t sak,
       } else {
         float v = acc[i][j] * rs;
         if (epi.bias) v += epi.bias[n] * gate;
-        C[m * ldc + n] = v;
+        if (epi.split_width > 0) {
+          const int blk = (int)(n / epi.split_width);
+          if (blk == 0) v *= epi.split_scale0;
+          reinterpret_cast<__nv_bfloat16*>(epi.split_out[blk])[m * epi.split_width + (n - (int64_t)blk * epi.split_width)] =
+              __float2bfloat16(v);
+        } else {
+          C[m * ldc + n] = v;
+        }
       }
     }
   }

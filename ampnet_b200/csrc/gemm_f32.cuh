@@ -11,6 +11,11 @@ struct GemmEpilogue {
   const float* bias_gate = nullptr;  // [M / rows_per_group] multiplies the bias
   const float* row_scale = nullptr;  // [M / rows_per_group] multiplies the whole row
   int rows_per_group = 1;
+  // optional bf16 output split into column blocks of `split_width`: block j of row m goes to
+  // split_out[j][m * split_width + n % split_width]; block 0 is multiplied by split_scale0.
+  void* split_out[3] = {nullptr, nullptr, nullptr};
+  int split_width = 0;
+  float split_scale0 = 1.f;
 };
 
 // Launches the GEMM on `stream`.  If splits > 1 the K range is divided and partial tiles go to

@@ -100,3 +100,19 @@ extern "C" int ampconv_qkv_proj_bwd_f32(const float* x, const float* d_qkv, cons
   if (rc != AMPCONV_OK) return rc;
   return colsum_f32(d_qkv, d3, rows, d3, nullptr, 1, d_b, col_partials, kColsumPartials, stream);
 }
+
+// bf16 family: Q' = (x Wq^T + bq) * q_scale, K, V as three bf16 [rows, d] tensors (node-major tiles for TMA).
+extern "C" int ampconv_qkv_proj_bf16(const float* x, const float* w, const float* b, void* q, void* k, void* v,
+                                     int64_t rows, int d, float q_scale, void* stream) {
+  AMPCONV_REQUIRE(rows >= 0 && d > 0);
+  if (rows == 0) return AMPCONV_OK;
+  AMPCONV_REQUIRE(x && w && b && q && k && v);
+  GemmEpilogue epi;
+  epi.bias = b;
+  epi.split_out[0] = q;
+  epi.split_out[1] = k;
+  epi.split_out[2] = v;
+  epi.split_width = d;
+  epi.split_scale0 = q_scale;
+  return gemm_f32(x, d, 1, w, 1, d, nullptr, 0, rows, 3 * (int64_t)d, d, epi, 1, nullptr, as_stream(stream));
+}

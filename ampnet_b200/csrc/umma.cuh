@@ -55,12 +55,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Spins until the phase with the given parity completes.  `budget` bounds the spin so that a
-// protocol bug turns into a reported failure (returns false) instead of a hung GPU.
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, uint32_t budget = 0x7fffffffu) {
-  for (uint32_t i = 0; i < budget; ++i)
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// Waits until the phase with the given parity completes.  The wait is bounded (budget_ns of wall
+// time, default 0.25 s) so that a protocol bug turns into a reported failure (returns false)
+// instead of a hung GPU; legitimate waits in these kernels last microseconds.
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, uint64_t budget_ns = 250000000ull) {
+  for (int i = 0; i < 1024; ++i)
     if (mbar_try_wait(bar, parity)) return true;
-  return false;
+  const uint64_t t0 = global_timer_ns();
+  for (;;) {
+    for (int i = 0; i < 256; ++i)
+      if (mbar_try_wait(bar, parity)) return true;
+    if (global_timer_ns() - t0 > budget_ns) return false;
+  }
 }
 
 // ------------------------------------------------------------------------------------------

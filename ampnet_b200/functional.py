@@ -11,7 +11,25 @@ import torch
 
 from . import _lib
 
-MODES = ("fp32",)
+MODES = ("fp32", "bf16", "auto")
+LOG2E = 1.4426950408889634
+LN2 = 0.6931471805599453
+
+
+def bf16_supported(f, d, h):
+    lib = _lib.load()
+    return bool(lib.ampconv_attn_bf16_supported(int(f), int(d), int(h)))
+
+
+def resolve_mode(mode, f, d, h):
+    if mode not in MODES:
+        raise ValueError(f"unknown mode {mode!r}; available: {MODES}")
+    if mode == "auto":
+        return "bf16" if bf16_supported(f, d, h) else "fp32"
+    if mode == "bf16" and not bf16_supported(f, d, h):
+        raise ValueError(f"mode='bf16' (tcgen05 kernels) does not cover F={f}, embed_dim={d}, num_heads={h}; "
+                         "use mode='auto' or 'fp32'")
+    return mode
 
 
 def _stream(dev):
@@ -27,9 +45,23 @@ def _param_grad_ws(out_dim, in_dim, dev):
 class _Saved:
     """What the last forward of a layer keeps for backward and for the lazy side outputs."""
 
-    def __init__(self, mode, graph, shape, qkv, agg, lse):
+    def __init__(self, mode, graph, shape, qkv, agg, lse, bf16=None, inputs=None):
         self.mode, self.graph, self.shape = mode, graph, shape
         self.qkv, self.agg, self.lse = qkv, agg, lse
+        self.bf16 = bf16          # (q, k, v, lse2) of the tensor-core family
+        self.inputs = inputs      # (x, w_in, b_in): lets the fp32 views be rebuilt lazily
+
+    def ensure_fp32_views(self):
+        """fp32 qkv and natural-log lse (needed by the fp32 kernels) for a forward that ran in bf16 mode."""
+        if self.qkv is None:
+            x, w_in, b_in = self.inputs
+            n, e, f, d, h = self.shape
+            dev = x.device
+            self.qkv = torch.empty((n * f, 3 * d), dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                _lib.call("ampconv_qkv_proj_f32", x, w_in, b_in, self.qkv, _lib.i64(n * f), _lib.i32(d), _stream(dev))
+            self.lse = self.bf16[3] * LN2
+        return self
 
 
 def _forward_fp32(x, graph, w_in, b_in, w_out, b_out, num_heads):
@@ -52,7 +84,37 @@ def _forward_fp32(x, graph, w_in, b_in, w_out, b_out, num_heads):
     return out, _Saved("fp32", graph, (n, e, f, d, num_heads), qkv, agg, lse)
 
 
+def _forward_bf16(x, graph, w_in, b_in, w_out, b_out, num_heads):
+    """tcgen05 forward: node-level projection to bf16 Q'/K/V, fused attention + mean on tensor cores."""
+    n, width = x.shape
+    d = w_in.shape[1]
+    f = width // d
+    dev = x.device
+    e = graph.num_edges
+    st = _stream(dev)
+    rows = n * f
+    hd = d // num_heads
+    q = torch.empty((rows, d), dtype=torch.bfloat16, device=dev)
+    k = torch.empty_like(q)
+    v = torch.empty_like(q)
+    agg = torch.empty((rows, d), dtype=torch.float32, device=dev)
+    lse2 = torch.empty((e, num_heads, f), dtype=torch.float32, device=dev)
+    out = torch.empty((n, width), dtype=torch.float32, device=dev)
+    ws = torch.zeros(64, dtype=torch.int32, device=dev)
+    _lib.call("ampconv_qkv_proj_bf16", x, w_in, b_in, q, k, v, _lib.i64(rows), _lib.i32(d),
+              _lib.f32(LOG2E / hd ** 0.5), st)
+    _lib.call("ampconv_attn_fwd_bf16", q, k, v, graph.dst_rowptr, graph.dst_src, graph.inv_deg, None, agg, lse2,
+              _lib.i64(n), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(num_heads),
+              ws, _lib.size_t(ws.numel() * 4), st)
+    _lib.call("ampconv_out_proj_f32", agg, w_out, b_out, graph.has_in, out,
+              _lib.i64(n), _lib.i32(f), _lib.i32(d), st)
+    saved = _Saved("bf16", graph, (n, e, f, d, num_heads), None, agg, None, bf16=(q, k, v, lse2, ws),
+                   inputs=(x, w_in.detach(), b_in.detach()))
+    return out, saved
+
+
 def _backward_fp32(saved, x, w_in, w_out, d_out):
+    saved.ensure_fp32_views()
     n, e, f, d, h = saved.shape
     g = saved.graph
     dev = x.device
@@ -84,7 +146,8 @@ class _AMPConvFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w_in, b_in, w_out, b_out, graph, num_heads, mode, holder):
         with torch.cuda.device(x.device):
-            out, saved = _forward_fp32(x, graph, w_in, b_in, w_out, b_out, num_heads)
+            fwd = _forward_bf16 if mode == "bf16" else _forward_fp32
+            out, saved = fwd(x, graph, w_in, b_in, w_out, b_out, num_heads)
         ctx.save_for_backward(x, w_in, w_out)
         ctx.saved_state = saved
         if holder is not None:
@@ -118,14 +181,14 @@ def check_inputs(x, edge_index, embed_dim, num_heads):
 
 
 def amp_conv(x, graph, w_in, b_in, w_out, b_out, num_heads, mode="fp32", holder=None):
-    if mode not in MODES:
-        raise ValueError(f"unknown mode {mode!r}; available: {MODES}")
+    mode = resolve_mode(mode, x.shape[1] // w_in.shape[1], w_in.shape[1], num_heads)
     return _AMPConvFunction.apply(x.contiguous(), w_in.contiguous(), b_in.contiguous(), w_out.contiguous(),
                                   b_out.contiguous(), graph, num_heads, mode, holder)
 
 
 def attention_weights(saved):
     """Head-averaged coefficients [E, F, F] in original edge order (``attn_output_weights``)."""
+    saved.ensure_fp32_views()
     n, e, f, d, h = saved.shape
     g = saved.graph
     dev = saved.qkv.device
@@ -138,6 +201,7 @@ def attention_weights(saved):
 
 def edge_output(saved, w_out, b_out):
     """Per-edge attention output after out_proj [E, F, d] in original edge order (``attn_output``)."""
+    saved.ensure_fp32_views()
     n, e, f, d, h = saved.shape
     g = saved.graph
     dev = saved.qkv.device
@@ -149,7 +213,7 @@ def edge_output(saved, w_out, b_out):
 
 
 def profile_stages(x, graph, w_in, b_in, w_out, b_out, num_heads, d_out, mode, reps):
-    """Per-kernel durations (ms) of the three attention kernels, each timed alone with CUDA events on
+    """Per-kernel durations (ms) of the attention kernels, each timed alone with CUDA events on
     the stream it is launched on (used by bench.py for the roofline line)."""
     n, width = x.shape
     d = w_in.shape[1]
@@ -157,9 +221,12 @@ def profile_stages(x, graph, w_in, b_in, w_out, b_out, num_heads, d_out, mode, r
     dev = x.device
     e = graph.num_edges
     rows = n * f
+    mode = resolve_mode(mode, f, d, num_heads)
     with torch.cuda.device(dev):
         st = _stream(dev)
-        out, saved = _forward_fp32(x, graph, w_in, b_in, w_out, b_out, num_heads)
+        fwd = _forward_bf16 if mode == "bf16" else _forward_fp32
+        out, saved = fwd(x, graph, w_in, b_in, w_out, b_out, num_heads)
+        saved.ensure_fp32_views()
         d_agg = torch.empty((rows, d), dtype=torch.float32, device=dev)
         d_w_out = torch.empty_like(w_out)
         d_b_out = torch.empty(d, dtype=torch.float32, device=dev)
@@ -169,14 +236,20 @@ def profile_stages(x, graph, w_in, b_in, w_out, b_out, num_heads, d_out, mode, r
         d_qkv = torch.empty((rows, 3 * d), dtype=torch.float32, device=dev)
         delta = torch.empty_like(saved.lse)
         dims = (_lib.i64(n), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(num_heads), st)
-        calls = {
-            "attn_fwd": lambda: _lib.call("ampconv_attn_fwd_f32", saved.qkv, graph.dst_rowptr, graph.dst_src,
-                                          graph.inv_deg, saved.agg, saved.lse, *dims),
-            "attn_bwd_dq": lambda: _lib.call("ampconv_attn_bwd_dq_f32", saved.qkv, d_agg, saved.lse, graph.dst_rowptr,
-                                             graph.dst_src, d_qkv, delta, *dims),
-            "attn_bwd_dkv": lambda: _lib.call("ampconv_attn_bwd_dkv_f32", saved.qkv, d_agg, saved.lse, delta,
-                                              graph.src_rowptr, graph.src_dst, graph.src_pos, d_qkv, *dims),
-        }
+        calls = {}
+        if mode == "bf16":
+            q, k, v, lse2, bws = saved.bf16
+            calls["attn_fwd"] = lambda: _lib.call(
+                "ampconv_attn_fwd_bf16", q, k, v, graph.dst_rowptr, graph.dst_src, graph.inv_deg, None, saved.agg, lse2,
+                _lib.i64(n), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(num_heads), bws,
+                _lib.size_t(bws.numel() * 4), st)
+        else:
+            calls["attn_fwd"] = lambda: _lib.call("ampconv_attn_fwd_f32", saved.qkv, graph.dst_rowptr, graph.dst_src,
+                                                  graph.inv_deg, saved.agg, saved.lse, *dims)
+        calls["attn_bwd_dq"] = lambda: _lib.call("ampconv_attn_bwd_dq_f32", saved.qkv, d_agg, saved.lse,
+                                                 graph.dst_rowptr, graph.dst_src, d_qkv, delta, *dims)
+        calls["attn_bwd_dkv"] = lambda: _lib.call("ampconv_attn_bwd_dkv_f32", saved.qkv, d_agg, saved.lse, delta,
+                                                  graph.src_rowptr, graph.src_dst, graph.src_pos, d_qkv, *dims)
         result = {}
         for name, fn in calls.items():
             fn()
@@ -189,3 +262,12 @@ def profile_stages(x, graph, w_in, b_in, w_out, b_out, num_heads, d_out, mode, r
             torch.cuda.synchronize()
             result[name] = e0.elapsed_time(e1) / reps
     return result
+
+
+def bf16_status(saved):
+    """Status word of the tensor-core kernels of a bf16-mode forward (0 = ok); synchronises."""
+    ws = saved.bf16[4]
+    status = ctypes.c_int(0)
+    with torch.cuda.device(ws.device):
+        _lib.call("ampconv_bf16_status", ws, ctypes.byref(status), _stream(ws.device))
+    return status.value

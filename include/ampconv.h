@@ -149,6 +149,35 @@ AMPCONV_API int ampconv_qkv_proj_bwd_f32(const float* x, const float* d_qkv, con
 
 AMPCONV_API int ampconv_param_grad_workspace_bytes(int out_dim, int in_dim, size_t* bytes);
 
+/* ------------------------------------------------------------------------------------------
+ * bf16 tensor-core family (tcgen05 + TMEM + TMA; d = 64, head_dim 16 or 32, F <= 128).
+ * Parity bar 2e-2 relative (BASELINE.json north_star, "bf16 mode").
+ * ------------------------------------------------------------------------------------------ */
+
+/* 1 if the tcgen05 kernels cover this shape, else 0 (callers then use the fp32 family). */
+AMPCONV_API int ampconv_attn_bf16_supported(int F, int d, int H);
+
+/* Node-level in-projection (custom_multihead_attn_forward.py:4031-4084) emitting three bf16
+ * [rows, d] tensors; q is additionally multiplied by q_scale (= log2(e)/sqrt(hd): the q*hd^-1/2
+ * of :4173 folded together with the base-2 softmax). */
+AMPCONV_API int ampconv_qkv_proj_bf16(const float* x, const float* in_proj_weight, const float* in_proj_bias,
+                          void* q, void* k, void* v, int64_t rows, int d, float q_scale, void* stream);
+
+/* Fused attention + mean aggregation on tensor cores (same contract as ampconv_attn_fwd_f32).
+ * q/k/v: bf16 [N,F,d] from ampconv_qkv_proj_bf16; agg: fp32 [N,F,d];
+ * lse2[p,h,i] = log2-sum-exp2 of the (log2-domain) scores of edge slot p;
+ * order: optional node processing order [N] (NULL = 0..N-1); workspace >= 256 bytes (scheduler counter
+ * and a status word, see ampconv_bf16_status). */
+AMPCONV_API int ampconv_attn_fwd_bf16(const void* q, const void* k, const void* v,
+                          const int32_t* dst_rowptr, const int32_t* dst_src, const float* inv_deg,
+                          const int32_t* order, float* agg, float* lse2,
+                          int64_t num_nodes, int64_t num_edges, int F, int d, int H,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* Copies the status word of the last bf16 kernel that used `workspace` to the host (0 = ok, otherwise
+ * the id of the pipeline wait that timed out).  Synchronises `stream`; meant for tests and debugging. */
+AMPCONV_API int ampconv_bf16_status(const void* workspace, int* status_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

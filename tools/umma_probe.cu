@@ -91,7 +91,7 @@ probe_kernel(Params p, const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16*
       tma_load_3d(sA, &mapQ, &bar_tma, 0, 0, 1);
       if (p.mode == 4) tma_load_3d(sB, &mapK, &bar_tma, 0, 0, 1);
     }
-    ok = mbar_wait(&bar_tma, 0, 20000000u);
+    ok = mbar_wait(&bar_tma, 0);
     if (!ok && tid == 0) atomicExch(status, 1);
   }
   tc_fence_before();
@@ -120,7 +120,7 @@ probe_kernel(Params p, const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16*
       }
       mma_commit(&bar_mma);
     }
-    ok = mbar_wait(&bar_mma, 0, 20000000u);
+    ok = mbar_wait(&bar_mma, 0);
     if (!ok && tid == 0) atomicExch(status, 2);
     tc_fence_after();
     if (ok) {
