@@ -313,7 +313,7 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&sm.p_full[b]);
-          if (row_ok) lse2[((int64_t)p * H + h) * F + row] = m + __log2f(l);
+          if (row_ok) lse2[((int64_t)p * H + h) * ((F + 3) & ~3) + row] = m + __log2f(l);
           if (t > 0) {
             if (!consume(c - 1, (hl + HL - 1) % HL, l_prev)) AMP_FAIL(304);
           }

@@ -44,10 +44,10 @@ extern "C" int ampconv_out_proj_f32(const float* agg, const float* w, const floa
   return gemm_f32(agg, d, 1, w, 1, d, out, d, N * F, d, d, epi, 1, nullptr, as_stream(stream));
 }
 
-extern "C" int ampconv_out_proj_bwd_f32(const float* d_out, const float* agg, const float* w,
-                                        const float* inv_deg, const float* has_in,
-                                        float* d_agg, float* d_w, float* d_b,
-                                        int64_t N, int F, int d, void* ws, size_t ws_bytes, void* stream_) {
+static int out_proj_bwd_impl(const float* d_out, const float* agg, const float* w,
+                             const float* inv_deg, const float* has_in,
+                             float* d_agg, void* d_agg_bf16, float* d_w, float* d_b,
+                             int64_t N, int F, int d, void* ws, size_t ws_bytes, void* stream_) {
   AMPCONV_REQUIRE(N >= 0 && F > 0 && d > 0 && d_w && d_b);
   cudaStream_t stream = as_stream(stream_);
   const int64_t rows = N * F;
@@ -56,7 +56,7 @@ extern "C" int ampconv_out_proj_bwd_f32(const float* d_out, const float* agg, co
     AMPCONV_CUDA_TRY(cudaMemsetAsync(d_b, 0, sizeof(float) * d, stream));
     return AMPCONV_OK;
   }
-  AMPCONV_REQUIRE(d_out && agg && w && inv_deg && has_in && d_agg && ws);
+  AMPCONV_REQUIRE(d_out && agg && w && inv_deg && has_in && (d_agg || d_agg_bf16) && ws);
   const int splits = choose_splits(d, d, rows);
   const size_t need = (ws_split_floats(d, d, splits) + (size_t)kColsumPartials * d) * sizeof(float);
   if (need > ws_bytes) return AMPCONV_ERR_WORKSPACE;
@@ -66,6 +66,10 @@ extern "C" int ampconv_out_proj_bwd_f32(const float* d_out, const float* agg, co
   GemmEpilogue epi;
   epi.row_scale = inv_deg;
   epi.rows_per_group = F;
+  if (d_agg_bf16) {
+    epi.split_out[0] = d_agg_bf16;
+    epi.split_width = d;
+  }
   int rc = gemm_f32(d_out, d, 1, w, d, 1, d_agg, d, rows, d, d, epi, 1, nullptr, stream);
   if (rc != AMPCONV_OK) return rc;
   // d_w[o,k] = sum_r d_out[r,o] * agg[r,k]
@@ -73,6 +77,20 @@ extern "C" int ampconv_out_proj_bwd_f32(const float* d_out, const float* agg, co
   if (rc != AMPCONV_OK) return rc;
   // d_b[o] = sum over rows whose node has an in-edge
   return colsum_f32(d_out, d, rows, d, has_in, F, d_b, col_partials, kColsumPartials, stream);
+}
+
+extern "C" int ampconv_out_proj_bwd_f32(const float* d_out, const float* agg, const float* w,
+                                        const float* inv_deg, const float* has_in,
+                                        float* d_agg, float* d_w, float* d_b,
+                                        int64_t N, int F, int d, void* ws, size_t ws_bytes, void* stream_) {
+  return out_proj_bwd_impl(d_out, agg, w, inv_deg, has_in, d_agg, nullptr, d_w, d_b, N, F, d, ws, ws_bytes, stream_);
+}
+
+extern "C" int ampconv_out_proj_bwd_bf16(const float* d_out, const float* agg, const float* w,
+                                         const float* inv_deg, const float* has_in,
+                                         void* d_agg_bf16, float* d_w, float* d_b,
+                                         int64_t N, int F, int d, void* ws, size_t ws_bytes, void* stream_) {
+  return out_proj_bwd_impl(d_out, agg, w, inv_deg, has_in, nullptr, d_agg_bf16, d_w, d_b, N, F, d, ws, ws_bytes, stream_);
 }
 
 extern "C" int ampconv_qkv_proj_bwd_f32(const float* x, const float* d_qkv, const float* w,

@@ -60,7 +60,7 @@ class _Saved:
             self.qkv = torch.empty((n * f, 3 * d), dtype=torch.float32, device=dev)
             with torch.cuda.device(dev):
                 _lib.call("ampconv_qkv_proj_f32", x, w_in, b_in, self.qkv, _lib.i64(n * f), _lib.i32(d), _stream(dev))
-            self.lse = self.bf16[3] * LN2
+            self.lse = (self.bf16[3][:, :, :f] * LN2).contiguous()
         return self
 
 
@@ -98,7 +98,7 @@ def _forward_bf16(x, graph, w_in, b_in, w_out, b_out, num_heads):
     k = torch.empty_like(q)
     v = torch.empty_like(q)
     agg = torch.empty((rows, d), dtype=torch.float32, device=dev)
-    lse2 = torch.empty((e, num_heads, f), dtype=torch.float32, device=dev)
+    lse2 = torch.empty((e, num_heads, (f + 3) // 4 * 4), dtype=torch.float32, device=dev)
     out = torch.empty((n, width), dtype=torch.float32, device=dev)
     ws = torch.zeros(64, dtype=torch.int32, device=dev)
     _lib.call("ampconv_qkv_proj_bf16", x, w_in, b_in, q, k, v, _lib.i64(rows), _lib.i32(d),
@@ -142,6 +142,38 @@ def _backward_fp32(saved, x, w_in, w_out, d_out):
     return d_x, d_w_in, d_b_in, d_w_out, d_b_out
 
 
+def _backward_bf16(saved, x, w_in, w_out, d_out):
+    """tcgen05 backward: dO tile in bf16, two recompute kernels (dQ by destination, dK/dV by source)."""
+    n, e, f, d, h = saved.shape
+    g = saved.graph
+    dev = x.device
+    st = _stream(dev)
+    rows = n * f
+    q, k, v, lse2, bws = saved.bf16
+    d_out = d_out.contiguous()
+    d_agg = torch.empty((rows, d), dtype=torch.bfloat16, device=dev)
+    d_w_out = torch.empty_like(w_out)
+    d_b_out = torch.empty(d, dtype=torch.float32, device=dev)
+    ws = _param_grad_ws(3 * d, d, dev)
+    _lib.call("ampconv_out_proj_bwd_bf16", d_out, saved.agg, w_out, g.inv_deg, g.has_in,
+              d_agg, d_w_out, d_b_out, _lib.i64(n), _lib.i32(f), _lib.i32(d), ws, _lib.size_t(ws.numel()), st)
+    d_qkv = torch.empty((rows, 3 * d), dtype=torch.float32, device=dev)
+    delta = torch.empty_like(lse2)
+    tail = (_lib.i64(n), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(h), bws, _lib.size_t(bws.numel() * 4), st)
+    _lib.call("ampconv_attn_bwd_dq_bf16", q, k, v, d_agg, lse2, g.dst_rowptr, g.dst_src, d_qkv, delta, *tail)
+    _lib.call("ampconv_attn_bwd_dkv_bf16", q, k, v, d_agg, lse2, delta, g.src_rowptr, g.src_dst, g.src_pos,
+              d_qkv, *tail)
+    d_x = torch.empty_like(x)
+    d_w_in = torch.empty_like(w_in)
+    d_b_in = torch.empty(3 * d, dtype=torch.float32, device=dev)
+    _lib.call("ampconv_qkv_proj_bwd_f32", x, d_qkv, w_in, d_x, d_w_in, d_b_in,
+              _lib.i64(rows), _lib.i32(d), ws, _lib.size_t(ws.numel()), st)
+    return d_x, d_w_in, d_b_in, d_w_out, d_b_out
+
+
+BF16_BACKWARD = "tcgen05"   # "fp32" routes the backward of a bf16-mode forward through the fp32 kernels (debug aid)
+
+
 class _AMPConvFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w_in, b_in, w_out, b_out, graph, num_heads, mode, holder):
@@ -159,7 +191,8 @@ class _AMPConvFunction(torch.autograd.Function):
     def backward(ctx, d_out):
         x, w_in, w_out = ctx.saved_tensors
         with torch.cuda.device(x.device):
-            d_x, d_w_in, d_b_in, d_w_out, d_b_out = _backward_fp32(ctx.saved_state, x, w_in, w_out, d_out)
+            bwd = _backward_bf16 if (ctx.saved_state.mode == "bf16" and BF16_BACKWARD == "tcgen05") else _backward_fp32
+            d_x, d_w_in, d_b_in, d_w_out, d_b_out = bwd(ctx.saved_state, x, w_in, w_out, d_out)
         return d_x, d_w_in, d_b_in, d_w_out, d_b_out, None, None, None, None
 
 

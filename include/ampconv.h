@@ -165,7 +165,7 @@ AMPCONV_API int ampconv_qkv_proj_bf16(const float* x, const float* in_proj_weigh
 
 /* Fused attention + mean aggregation on tensor cores (same contract as ampconv_attn_fwd_f32).
  * q/k/v: bf16 [N,F,d] from ampconv_qkv_proj_bf16; agg: fp32 [N,F,d];
- * lse2[p,h,i] = log2-sum-exp2 of the (log2-domain) scores of edge slot p;
+ * lse2[p,h,i] = log2-sum-exp2 of the (log2-domain) scores of edge slot p, shape [E, H, roundup4(F)];
  * order: optional node processing order [N] (NULL = 0..N-1); workspace >= 256 bytes (scheduler counter
  * and a status word, see ampconv_bf16_status). */
 AMPCONV_API int ampconv_attn_fwd_bf16(const void* q, const void* k, const void* v,
@@ -173,6 +173,29 @@ AMPCONV_API int ampconv_attn_fwd_bf16(const void* q, const void* k, const void* 
                           const int32_t* order, float* agg, float* lse2,
                           int64_t num_nodes, int64_t num_edges, int F, int d, int H,
                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of ampconv_out_proj_f32 for the bf16 family: identical, except that d_agg (already
+ * multiplied by inv_deg) is emitted as bf16 [N,F,d], the dO tile the tcgen05 backward kernels load. */
+AMPCONV_API int ampconv_out_proj_bwd_bf16(const float* d_out, const float* agg, const float* out_proj_weight,
+                              const float* inv_deg, const float* has_in,
+                              void* d_agg_bf16, float* d_w, float* d_b,
+                              int64_t num_nodes, int F, int d,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of ampconv_attn_fwd_bf16 on tensor cores (flash-style recompute from lse2), two kernels:
+ *   _dq : destination-sorted; writes d_qkv[:, 0:d] (fp32 [rows,3d]) and delta[p,h,i];
+ *   _dkv: source-sorted; reads delta; writes d_qkv[:, d:3d].
+ * lse2 / delta use a row stride of roundup4(F): shape [E, H, roundup4(F)].
+ * Same workspace as the forward call (>= 256 bytes). */
+AMPCONV_API int ampconv_attn_bwd_dq_bf16(const void* q, const void* k, const void* v, const void* d_agg_bf16,
+                             const float* lse2, const int32_t* dst_rowptr, const int32_t* dst_src,
+                             float* d_qkv, float* delta, int64_t num_nodes, int64_t num_edges, int F, int d, int H,
+                             void* workspace, size_t workspace_bytes, void* stream);
+AMPCONV_API int ampconv_attn_bwd_dkv_bf16(const void* q, const void* k, const void* v, const void* d_agg_bf16,
+                              const float* lse2, const float* delta, const int32_t* src_rowptr,
+                              const int32_t* src_dst, const int32_t* src_pos, float* d_qkv,
+                              int64_t num_nodes, int64_t num_edges, int F, int d, int H,
+                              void* workspace, size_t workspace_bytes, void* stream);
 
 /* Copies the status word of the last bf16 kernel that used `workspace` to the host (0 = ok, otherwise
  * the id of the pipeline wait that timed out).  Synchronises `stream`; meant for tests and debugging. */
