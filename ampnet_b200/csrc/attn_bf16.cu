@@ -65,13 +65,13 @@ struct FwdSmem {
     if (!mbar_wait((bar), (parity))) AMP_FAIL(code);        \
   } while (0)
 
-template <int HD>
+template <int HD, bool PROF>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                      const __grid_constant__ CUtensorMap mapV, const int32_t* __restrict__ rowptr,
                      const int32_t* __restrict__ dst_src, const float* __restrict__ inv_deg,
                      const int32_t* __restrict__ order, int* __restrict__ counter, int* __restrict__ status,
-                     float* __restrict__ agg, float* __restrict__ lse2, int N, int F) {
+                     float* __restrict__ agg, float* __restrict__ lse2, int N, int F, long long* __restrict__ prof) {
   constexpr int H = kD / HD;        // heads
   constexpr int HL = H / 2;         // heads per softmax warpgroup (head h belongs to warpgroup h & 1)
   static_assert(H % 2 == 0, "this kernel splits heads between two warpgroups");
@@ -83,14 +83,14 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sm.q_full[i], 1);
-      mbar_init(&sm.q_empty[i], 1 + 256);
+      mbar_init(&sm.q_empty[i], 1 + 8);
       mbar_init(&sm.s_full[i], 1);
-      mbar_init(&sm.s_empty[i], 128);
-      mbar_init(&sm.p_full[i], 128);
+      mbar_init(&sm.s_empty[i], 4);
+      mbar_init(&sm.p_full[i], 4);
       mbar_init(&sm.p_empty[i], 1);
       for (int j = 0; j < 2; ++j) {
         mbar_init(&sm.o_full[i][j], 1);
-        mbar_init(&sm.o_empty[i][j], 128);
+        mbar_init(&sm.o_empty[i][j], 4);
       }
     }
     for (int i = 0; i < kStages; ++i) {
@@ -175,41 +175,58 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
     }
   } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
+    // Two cursors over the global item sequence (item = edge * H + head): the score MMAs run ahead as far as
+    // the S buffers allow, the P V MMAs follow as soon as a warpgroup has published P.  Every wait of the
+    // score cursor keeps servicing the P V cursor, so neither can starve the other.
     if (lane == 0) {
       const uint32_t idesc_qk = idesc_bf16(128, nqk, 0, 0);
       const uint32_t idesc_pv = idesc_bf16(128, HD, 0, 1);
-      uint32_t qi = 0, ei = 0, c[2] = {0, 0};
-      bool have_prev = false;
-      uint32_t pv_b = 0, pv_st = 0, pv_h = 0, pv_c = 0;
-      bool pv_last = false;
-      auto issue_pv = [&]() -> bool {
-        if (!mbar_wait(&sm.p_full[pv_b], pv_c & 1)) return false;
-        const uint32_t ob = pv_c & 1;
-        if (!mbar_wait(&sm.o_empty[pv_b][ob], ((pv_c >> 1) & 1) ^ 1)) return false;
+      uint32_t qi = 0, g_qk = 0, g_pv = 0;
+      auto service_pv = [&]() -> bool {
+        if (g_pv >= g_qk) return false;
+        const uint32_t h = g_pv % H, edge = g_pv / H, b = h & 1;
+        const uint32_t cc = edge * HL + (h >> 1), ob = cc & 1, st = edge % kStages;
+        if (!mbar_test_wait(&sm.p_full[b], cc & 1)) return false;
+        if (!mbar_test_wait(&sm.o_empty[b][ob], ((cc >> 1) & 1) ^ 1)) return false;
         tc_fence_after();
-        const uint32_t v_base = smem_u32(sm.kv[pv_st][1]) + pv_h * (HD * 2);
-        const uint32_t o_col = tmem + 384 + (2 * pv_b + ob) * HD;
-        const uint32_t p_col = tmem + 256 + pv_b * 64;
+        const uint32_t v_base = smem_u32(sm.kv[st][1]) + h * (HD * 2);
+        const uint32_t o_col = tmem + 384 + (2 * b + ob) * HD;
+        const uint32_t p_col = tmem + 256 + b * 64;
         for (int ks = 0; ks < ksteps; ++ks)
           mma_ts(o_col, p_col + 8 * ks, smem_desc(v_base + ks * 2048, 16, 1024, LAYOUT_SW128), idesc_pv, ks > 0);
-        mma_commit(&sm.o_full[pv_b][ob]);
-        mma_commit(&sm.p_empty[pv_b]);
-        if (pv_last) mma_commit(&sm.kv_empty[pv_st]);
+        mma_commit(&sm.o_full[b][ob]);
+        mma_commit(&sm.p_empty[b]);
+        if (h == H - 1) mma_commit(&sm.kv_empty[st]);
+        ++g_pv;
         return true;
+      };
+      auto wait_serving = [&](uint64_t* bar, uint32_t parity) -> bool {
+        uint64_t t0 = 0;
+        for (uint32_t spins = 0;; ++spins) {
+          if (mbar_test_wait(bar, parity)) return true;
+          if (service_pv()) { t0 = 0; continue; }
+          __nanosleep(20);
+          if ((spins & 255) == 255) {
+            const uint64_t now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 250000000ull) return false;
+          }
+        }
       };
       for (;;) {
         const uint32_t qb = qi & 1;
-        AMP_WAIT(&sm.q_full[qb], (qi >> 1) & 1, 201);
+        if (!wait_serving(&sm.q_full[qb], (qi >> 1) & 1)) AMP_FAIL(201);
         const NodeSlot ns = sm.slot[qb];
         if (ns.node < 0) break;
         if (ns.p_end == ns.p_begin) mbar_arrive(&sm.q_empty[qb]);
-        for (int p = ns.p_begin; p < ns.p_end; ++p, ++ei) {
-          const uint32_t st = ei % kStages;
-          AMP_WAIT(&sm.kv_full[st], (ei / kStages) & 1, 202);
+        for (int p = ns.p_begin; p < ns.p_end; ++p) {
+          const uint32_t edge = g_qk / H, st = edge % kStages;
+          if (!wait_serving(&sm.kv_full[st], (edge / kStages) & 1)) AMP_FAIL(202);
 #pragma unroll
           for (int h = 0; h < H; ++h) {
             const uint32_t b = h & 1;
-            AMP_WAIT(&sm.s_empty[b], (c[b] & 1) ^ 1, 203);
+            const uint32_t cc = edge * HL + (h >> 1);
+            if (!wait_serving(&sm.s_empty[b], (cc & 1) ^ 1)) AMP_FAIL(203);
             tc_fence_after();
             const uint32_t qa = smem_u32(sm.q[qb]) + h * (HD * 2);
             const uint32_t ka = smem_u32(sm.kv[st][0]) + h * (HD * 2);
@@ -219,15 +236,19 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
                      smem_desc(ka + ks * 32, 16, 1024, LAYOUT_SW128), idesc_qk, ks > 0);
             mma_commit(&sm.s_full[b]);
             if (p + 1 == ns.p_end && h == H - 1) mma_commit(&sm.q_empty[qb]);
-            if (have_prev && !issue_pv()) AMP_FAIL(204);
-            pv_b = b; pv_st = st; pv_h = h; pv_c = c[b]; pv_last = (h == H - 1);
-            have_prev = true;
-            ++c[b];
+            ++g_qk;
+            service_pv();
           }
         }
         ++qi;
       }
-      if (have_prev && !issue_pv()) AMP_FAIL(205);
+      {
+        uint64_t t0 = global_timer_ns();
+        while (g_pv < g_qk) {
+          if (service_pv()) { t0 = global_timer_ns(); continue; }
+          if (global_timer_ns() - t0 > 250000000ull) AMP_FAIL(205);
+        }
+      }
     }
   } else {
     // ------------------------------------------------------------------ softmax warpgroups
@@ -237,11 +258,18 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t qi = 0, c = 0;
     float* acc = &sm.acc[0][b * 128 + row];   // element x of this thread: acc[x * 256]
+    // optional phase timers (debug entry point only): cycles spent by warp 0 of CTA 0 in each phase
+    const bool do_prof = PROF && blockIdx.x == 0;
+    long long pt[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tp = do_prof ? clock64() : 0;
+#define AMP_PHASE(i) do { if (do_prof) { const long long now_ = clock64(); pt[i] += now_ - tp; tp = now_; } } while (0)
     for (;;) {
       const uint32_t qb = qi & 1;
       AMP_WAIT(&sm.q_full[qb], (qi >> 1) & 1, 301);
+      AMP_PHASE(8);
       const NodeSlot ns = sm.slot[qb];
-      mbar_arrive(&sm.q_empty[qb]);   // slot contents are now in registers (256 of the 257 arrivals)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.q_empty[qb]);   // slot contents are in registers (8 of the 9 arrivals)
       if (ns.node < 0) break;
 #pragma unroll
       for (int x = 0; x < HL * HD; ++x) acc[x * 256] = 0.f;
@@ -252,6 +280,7 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
         const uint32_t ob = cc & 1;
         if (!mbar_wait(&sm.o_full[b][ob], (cc >> 1) & 1)) return false;
         tc_fence_after();
+        AMP_PHASE(6);
         uint32_t o[HD];
         if constexpr (HD == 16) {
           tmem_ld_32x32b_x16(lane_base + 384 + (2 * b + ob) * HD, o);
@@ -260,11 +289,13 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
         }
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(&sm.o_empty[b][ob]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.o_empty[b][ob]);
         const float inv_l = 1.0f / l;
         float* a = acc + hl_prev * HD * 256;
 #pragma unroll
         for (int x = 0; x < HD; ++x) a[x * 256] = fmaf(__uint_as_float(o[x]), inv_l, a[x * 256]);
+        AMP_PHASE(7);
         return true;
       };
       for (int p = ns.p_begin; p < ns.p_end; ++p) {
@@ -272,6 +303,7 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
         for (int hl = 0; hl < HL; ++hl) {
           const int h = 2 * hl + b;
           AMP_WAIT(&sm.s_full[b], c & 1, 302);
+          AMP_PHASE(0);
           tc_fence_after();
           uint32_t s[128];
 #pragma unroll
@@ -279,21 +311,27 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
             tmem_ld_32x32b_x32(lane_base + b * 128 + 32 * k, *reinterpret_cast<uint32_t(*)[32]>(&s[32 * k]));
           tmem_ld_wait();
           tc_fence_before();
-          mbar_arrive(&sm.s_empty[b]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.s_empty[b]);
+          AMP_PHASE(1);
           // mask source tokens >= F (their K rows are TMA zero fill, the score columns may be stale)
           if (F < 128) {
 #pragma unroll
             for (int j = 0; j < 128; ++j)
               if (j >= F) s[j] = __float_as_uint(-CUDART_INF_F);
           }
-          float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F;
+          float mx[8];
 #pragma unroll
-          for (int j = 0; j < 128; j += 2) {
-            m0 = fmaxf(m0, __uint_as_float(s[j]));
-            m1 = fmaxf(m1, __uint_as_float(s[j + 1]));
-          }
-          const float m = fmaxf(m0, m1);
+          for (int u = 0; u < 8; ++u) mx[u] = __uint_as_float(s[u]);
+#pragma unroll
+          for (int j = 8; j < 128; j += 8)
+#pragma unroll
+            for (int u = 0; u < 8; ++u) mx[u] = fmaxf(mx[u], __uint_as_float(s[j + u]));
+          const float m = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])),
+                                fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
+          AMP_PHASE(2);
           AMP_WAIT(&sm.p_empty[b], (c & 1) ^ 1, 303);
+          AMP_PHASE(3);
           tc_fence_after();
           float l0 = 0.f, l1 = 0.f;
 #pragma unroll
@@ -310,10 +348,13 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
             tmem_st_32x32b_x16(lane_base + 256 + b * 64 + 16 * k, pk);
           }
           const float l = l0 + l1;
+          AMP_PHASE(4);
           tmem_st_wait();
           tc_fence_before();
-          mbar_arrive(&sm.p_full[b]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.p_full[b]);
           if (row_ok) lse2[((int64_t)p * H + h) * ((F + 3) & ~3) + row] = m + __log2f(l);
+          AMP_PHASE(5);
           if (t > 0) {
             if (!consume(c - 1, (hl + HL - 1) % HL, l_prev)) AMP_FAIL(304);
           }
@@ -337,8 +378,14 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
                                      a[(x + 2) * 256] * ns.inv_deg, a[(x + 3) * 256] * ns.inv_deg);
         }
       }
+      AMP_PHASE(9);
       ++qi;
     }
+    if (do_prof && threadIdx.x == 0) {
+      for (int i = 0; i < 10; ++i) prof[i] = pt[i];
+      prof[10] = c;
+    }
+#undef AMP_PHASE
   }
 fail:
   tc_fence_before();
@@ -357,11 +404,11 @@ extern "C" int ampconv_attn_bf16_supported(int F, int d, int H) {
   return (hd == 16 || hd == 32) && F >= 1 && F <= 128;
 }
 
-extern "C" int ampconv_attn_fwd_bf16(const void* q, const void* k, const void* v,
-                                     const int32_t* dst_rowptr, const int32_t* dst_src, const float* inv_deg,
-                                     const int32_t* order, float* agg, float* lse2,
-                                     int64_t N, int64_t E, int F, int d, int H,
-                                     void* workspace, size_t workspace_bytes, void* stream_) {
+static int attn_fwd_bf16_impl(const void* q, const void* k, const void* v,
+                              const int32_t* dst_rowptr, const int32_t* dst_src, const float* inv_deg,
+                              const int32_t* order, float* agg, float* lse2,
+                              int64_t N, int64_t E, int F, int d, int H,
+                              void* workspace, size_t workspace_bytes, void* stream_, long long* prof) {
   AMPCONV_REQUIRE(N >= 0 && E >= 0 && F > 0 && d > 0 && H > 0 && d % H == 0);
   if (!ampconv_attn_bf16_supported(F, d, H)) return AMPCONV_ERR_UNSUPPORTED;
   if (N == 0) return AMPCONV_OK;
@@ -378,17 +425,42 @@ extern "C" int ampconv_attn_fwd_bf16(const void* q, const void* k, const void* v
   const size_t smem = sizeof(FwdSmem) + 1024;
   const int grid = (int)(N < sm_count() ? N : sm_count());
   const int hd = d / H;
+#define AMP_LAUNCH_FWD(HDV, PROFV)                                                                                    \
+  do {                                                                                                                \
+    AMPCONV_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_bf16_kernel<HDV, PROFV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          (int)smem));                                                                \
+    attn_fwd_bf16_kernel<HDV, PROFV><<<grid, kFwdThreads, smem, stream>>>(mq, mk, mv, dst_rowptr, dst_src, inv_deg, order, \
+                                                                         counter, status, agg, lse2, (int)N, F, prof);  \
+  } while (0)
   if (hd == 16) {
-    AMPCONV_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_bf16_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_fwd_bf16_kernel<16><<<grid, kFwdThreads, smem, stream>>>(mq, mk, mv, dst_rowptr, dst_src, inv_deg, order, counter,
-                                                                  status, agg, lse2, (int)N, F);
+    if (prof) AMP_LAUNCH_FWD(16, true); else AMP_LAUNCH_FWD(16, false);
   } else {
-    AMPCONV_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_bf16_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_fwd_bf16_kernel<32><<<grid, kFwdThreads, smem, stream>>>(mq, mk, mv, dst_rowptr, dst_src, inv_deg, order, counter,
-                                                                  status, agg, lse2, (int)N, F);
+    if (prof) AMP_LAUNCH_FWD(32, true); else AMP_LAUNCH_FWD(32, false);
   }
+#undef AMP_LAUNCH_FWD
   AMPCONV_CHECK_LAUNCH();
   return AMPCONV_OK;
+}
+
+extern "C" int ampconv_attn_fwd_bf16(const void* q, const void* k, const void* v,
+                                     const int32_t* dst_rowptr, const int32_t* dst_src, const float* inv_deg,
+                                     const int32_t* order, float* agg, float* lse2,
+                                     int64_t N, int64_t E, int F, int d, int H,
+                                     void* workspace, size_t workspace_bytes, void* stream_) {
+  return attn_fwd_bf16_impl(q, k, v, dst_rowptr, dst_src, inv_deg, order, agg, lse2, N, E, F, d, H, workspace,
+                            workspace_bytes, stream_, nullptr);
+}
+
+// Debug variant: additionally fills prof[0..10] (device, 11 x int64) with the cycles warp 0 of CTA 0 spent per
+// softmax phase (wait S, load S, max, wait P slot, exp+store, publish, wait O, accumulate, node wait, node epilogue)
+// and its item count.  Not part of the product path.
+extern "C" int ampconv_attn_fwd_bf16_profile(const void* q, const void* k, const void* v,
+                                             const int32_t* dst_rowptr, const int32_t* dst_src, const float* inv_deg,
+                                             const int32_t* order, float* agg, float* lse2,
+                                             int64_t N, int64_t E, int F, int d, int H,
+                                             void* workspace, size_t workspace_bytes, void* stream_, long long* prof) {
+  return attn_fwd_bf16_impl(q, k, v, dst_rowptr, dst_src, inv_deg, order, agg, lse2, N, E, F, d, H, workspace,
+                            workspace_bytes, stream_, prof);
 }
 
 // Reads back the protocol status word written by the bf16 kernels (0 = ok).  Synchronises the stream.

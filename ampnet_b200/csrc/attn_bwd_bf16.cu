@@ -90,15 +90,15 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sm.own_full[i], 1);
-      mbar_init(&sm.own_empty[i], 1 + 256);
+      mbar_init(&sm.own_empty[i], 1 + 8);
       mbar_init(&sm.xy_full[i], 1);
-      mbar_init(&sm.xy_empty[i], 128);
-      mbar_init(&sm.u_full[i], 128);
+      mbar_init(&sm.xy_empty[i], 4);
+      mbar_init(&sm.u_full[i], 4);
       mbar_init(&sm.t_full[i], 1);
     }
     for (int i = 0; i < NS; ++i) {
       mbar_init(&sm.edge_full[i], 1);
-      mbar_init(&sm.edge_empty[i], MODE == MODE_DKV ? 1 + 256 : 1);
+      mbar_init(&sm.edge_empty[i], MODE == MODE_DKV ? 1 + 8 : 1);
     }
     fence_barrier_init();
   }
@@ -190,40 +190,57 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
     }
   } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
+    // Two cursors over the global item sequence (item = edge * H + head): X/Y score MMAs and the T MMAs that
+    // consume the bf16 operands a warpgroup wrote back.  Waits of the first cursor keep servicing the second.
     if (lane == 0) {
       const uint32_t idesc_xy = idesc_bf16(128, nqk, 0, 0);
       const uint32_t idesc_t = idesc_bf16(128, HD, 0, 1);
-      uint32_t qi = 0, ei = 0, c[2] = {0, 0};
-      bool have_prev = false;
-      uint32_t t_b = 0, t_st = 0, t_h = 0, t_c = 0;
-      bool t_last = false;
-      // T MMAs of the previously issued item: TX = X' * B_tx, TY = Y' * B_ty (B operands MN-major)
-      auto issue_t = [&]() -> bool {
-        if (!mbar_wait(&sm.u_full[t_b], t_c & 1)) return false;
+      uint32_t qi = 0, g_xy = 0, g_t = 0;
+      // T MMAs: TX = X' * B_tx, TY = Y' * B_ty (B operands MN-major from the edge tiles)
+      auto service_t = [&]() -> bool {
+        if (g_t >= g_xy) return false;
+        const uint32_t h = g_t % H, edge = g_t / H, b = h & 1;
+        const uint32_t cc = edge * HL + (h >> 1), st = edge % NS;
+        if (!mbar_test_wait(&sm.u_full[b], cc & 1)) return false;
         tc_fence_after();
-        const uint32_t x_col = tmem + t_b * 256, y_col = x_col + 128;
-        const uint32_t btx = smem_u32(sm.edge[t_st][MODE == MODE_DQ ? 0 : 1]) + t_h * (HD * 2);
-        const uint32_t bty = smem_u32(sm.edge[t_st][0]) + t_h * (HD * 2);
+        const uint32_t x_col = tmem + b * 256, y_col = x_col + 128;
+        const uint32_t btx = smem_u32(sm.edge[st][MODE == MODE_DQ ? 0 : 1]) + h * (HD * 2);
+        const uint32_t bty = smem_u32(sm.edge[st][0]) + h * (HD * 2);
         for (int ks = 0; ks < ksteps; ++ks)
           mma_ts(x_col + 64, x_col + 8 * ks, smem_desc(btx + ks * 2048, 16, 1024, LAYOUT_SW128), idesc_t, ks > 0);
         for (int ks = 0; ks < ksteps; ++ks)
           mma_ts(y_col + 64, y_col + 8 * ks, smem_desc(bty + ks * 2048, 16, 1024, LAYOUT_SW128), idesc_t, ks > 0);
-        mma_commit(&sm.t_full[t_b]);
-        if (t_last) mma_commit(&sm.edge_empty[t_st]);
+        mma_commit(&sm.t_full[b]);
+        if (h == H - 1) mma_commit(&sm.edge_empty[st]);
+        ++g_t;
         return true;
+      };
+      auto wait_serving = [&](uint64_t* bar, uint32_t parity) -> bool {
+        uint64_t t0 = 0;
+        for (uint32_t spins = 0;; ++spins) {
+          if (mbar_test_wait(bar, parity)) return true;
+          if (service_t()) { t0 = 0; continue; }
+          __nanosleep(20);
+          if ((spins & 255) == 255) {
+            const uint64_t now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 250000000ull) return false;
+          }
+        }
       };
       for (;;) {
         const uint32_t qb = qi & 1;
-        AMP_WAIT(&sm.own_full[qb], (qi >> 1) & 1, 201);
+        if (!wait_serving(&sm.own_full[qb], (qi >> 1) & 1)) AMP_FAIL(201);
         const NodeSlot ns = sm.slot[qb];
         if (ns.node < 0) break;
-        for (int e = ns.e_begin; e < ns.e_end; ++e, ++ei) {
-          const uint32_t st = ei % NS;
-          AMP_WAIT(&sm.edge_full[st], (ei / NS) & 1, 202);
+        for (int e = ns.e_begin; e < ns.e_end; ++e) {
+          const uint32_t edge = g_xy / H, st = edge % NS;
+          if (!wait_serving(&sm.edge_full[st], (edge / NS) & 1)) AMP_FAIL(202);
 #pragma unroll
           for (int h = 0; h < H; ++h) {
             const uint32_t b = h & 1;
-            AMP_WAIT(&sm.xy_empty[b], (c[b] & 1) ^ 1, 203);
+            const uint32_t cc = edge * HL + (h >> 1);
+            if (!wait_serving(&sm.xy_empty[b], (cc & 1) ^ 1)) AMP_FAIL(203);
             tc_fence_after();
             const uint32_t hb = h * (HD * 2);
             const uint32_t a0 = smem_u32(sm.own[qb][0]) + hb, a1 = smem_u32(sm.own[qb][1]) + hb;
@@ -238,15 +255,19 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
                      smem_desc(b1 + ks * 32, 16, 1024, LAYOUT_SW128), idesc_xy, ks > 0);
             mma_commit(&sm.xy_full[b]);
             if (e + 1 == ns.e_end && h == H - 1) mma_commit(&sm.own_empty[qb]);
-            if (have_prev && !issue_t()) AMP_FAIL(204);
-            t_b = b; t_st = st; t_h = h; t_c = c[b]; t_last = (h == H - 1);
-            have_prev = true;
-            ++c[b];
+            ++g_xy;
+            service_t();
           }
         }
         ++qi;
       }
-      if (have_prev && !issue_t()) AMP_FAIL(205);
+      {
+        uint64_t t0 = global_timer_ns();
+        while (g_t < g_xy) {
+          if (service_t()) { t0 = global_timer_ns(); continue; }
+          if (global_timer_ns() - t0 > 250000000ull) AMP_FAIL(205);
+        }
+      }
     }
   } else {
     // ------------------------------------------------------------------ elementwise warpgroups
@@ -260,7 +281,8 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       const uint32_t qb = qi & 1;
       AMP_WAIT(&sm.own_full[qb], (qi >> 1) & 1, 301);
       const NodeSlot ns = sm.slot[qb];
-      mbar_arrive(&sm.own_empty[qb]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.own_empty[qb]);
       if (ns.node < 0) break;
 #pragma unroll
       for (int x = 0; x < Smem::NACC * HL * HD; ++x) acc[x * 256] = 0.f;
@@ -280,7 +302,8 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
         }
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(&sm.xy_empty[b]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.xy_empty[b]);
         float* a = acc + hl_prev * HD * 256;
         if (MODE == MODE_DQ) {
 #pragma unroll
@@ -299,6 +322,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       for (int e = ns.e_begin; e < ns.e_end; ++e, ++ei) {
         const uint32_t st = ei % NS;
         const int64_t sl = (MODE == MODE_DQ) ? (int64_t)e : 0;
+        if (MODE == MODE_DKV) AMP_WAIT(&sm.edge_full[st], (ei / NS) & 1, 306);   // acquire the bulk-copied statistics rows
 #pragma unroll
         for (int hl = 0; hl < HL; ++hl) {
           const int h = 2 * hl + b;
@@ -353,12 +377,14 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
           }
           tmem_st_wait();
           tc_fence_before();
-          mbar_arrive(&sm.u_full[b]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.u_full[b]);
           const float dl = dl0 + dl1;
           if (MODE == MODE_DQ) {
             if (row_ok) delta[(sl * H + h) * Fs + row] = dl;
           } else if (hl == HL - 1) {
-            mbar_arrive(&sm.edge_empty[st]);   // statistics rows of this stage are no longer needed by this thread
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.edge_empty[st]);   // this warp no longer reads the stage's statistics rows
           }
           dl_prev = dl;
           ++c;

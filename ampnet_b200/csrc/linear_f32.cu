@@ -134,3 +134,47 @@ extern "C" int ampconv_qkv_proj_bf16(const float* x, const float* w, const float
   epi.split_scale0 = q_scale;
   return gemm_f32(x, d, 1, w, 1, d, nullptr, 0, rows, 3 * (int64_t)d, d, epi, 1, nullptr, as_stream(stream));
 }
+
+// Parameter gradients only (the bf16 family computes the input gradients with the tcgen05 kernels of linear_tc.cu).
+extern "C" int ampconv_out_proj_bwd_params_f32(const float* d_out, const float* agg, const float* has_in,
+                                               float* d_w, float* d_b, int64_t N, int F, int d,
+                                               void* ws, size_t ws_bytes, void* stream_) {
+  AMPCONV_REQUIRE(N >= 0 && F > 0 && d > 0 && d_w && d_b);
+  cudaStream_t stream = as_stream(stream_);
+  const int64_t rows = N * F;
+  if (rows == 0) {
+    AMPCONV_CUDA_TRY(cudaMemsetAsync(d_w, 0, sizeof(float) * d * d, stream));
+    AMPCONV_CUDA_TRY(cudaMemsetAsync(d_b, 0, sizeof(float) * d, stream));
+    return AMPCONV_OK;
+  }
+  AMPCONV_REQUIRE(d_out && agg && has_in && ws);
+  const int splits = choose_splits(d, d, rows);
+  const size_t need = (ws_split_floats(d, d, splits) + (size_t)kColsumPartials * d) * sizeof(float);
+  if (need > ws_bytes) return AMPCONV_ERR_WORKSPACE;
+  float* partials = reinterpret_cast<float*>(ws);
+  float* col_partials = partials + ws_split_floats(d, d, splits);
+  int rc = gemm_f32(d_out, 1, d, agg, d, 1, d_w, d, d, d, rows, GemmEpilogue(), splits, partials, stream);
+  if (rc != AMPCONV_OK) return rc;
+  return colsum_f32(d_out, d, rows, d, has_in, F, d_b, col_partials, kColsumPartials, stream);
+}
+
+extern "C" int ampconv_qkv_proj_bwd_params_f32(const float* x, const float* d_qkv, float* d_w, float* d_b,
+                                               int64_t rows, int d, void* ws, size_t ws_bytes, void* stream_) {
+  AMPCONV_REQUIRE(rows >= 0 && d > 0 && d_w && d_b);
+  cudaStream_t stream = as_stream(stream_);
+  const int64_t d3 = 3 * (int64_t)d;
+  if (rows == 0) {
+    AMPCONV_CUDA_TRY(cudaMemsetAsync(d_w, 0, sizeof(float) * d3 * d, stream));
+    AMPCONV_CUDA_TRY(cudaMemsetAsync(d_b, 0, sizeof(float) * d3, stream));
+    return AMPCONV_OK;
+  }
+  AMPCONV_REQUIRE(x && d_qkv && ws);
+  const int splits = choose_splits(d3, d, rows);
+  const size_t need = (ws_split_floats((int)d3, d, splits) + (size_t)kColsumPartials * d3) * sizeof(float);
+  if (need > ws_bytes) return AMPCONV_ERR_WORKSPACE;
+  float* partials = reinterpret_cast<float*>(ws);
+  float* col_partials = partials + ws_split_floats((int)d3, d, splits);
+  int rc = gemm_f32(d_qkv, 1, d3, x, d, 1, d_w, d, d3, d, rows, GemmEpilogue(), splits, partials, stream);
+  if (rc != AMPCONV_OK) return rc;
+  return colsum_f32(d_qkv, d3, rows, d3, nullptr, 1, d_b, col_partials, kColsumPartials, stream);
+}

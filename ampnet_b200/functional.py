@@ -101,13 +101,13 @@ def _forward_bf16(x, graph, w_in, b_in, w_out, b_out, num_heads):
     lse2 = torch.empty((e, num_heads, (f + 3) // 4 * 4), dtype=torch.float32, device=dev)
     out = torch.empty((n, width), dtype=torch.float32, device=dev)
     ws = torch.zeros(64, dtype=torch.int32, device=dev)
-    _lib.call("ampconv_qkv_proj_bf16", x, w_in, b_in, q, k, v, _lib.i64(rows), _lib.i32(d),
-              _lib.f32(LOG2E / hd ** 0.5), st)
+    _lib.call("ampconv_qkv_proj_tc", x, w_in, b_in, q, k, v, _lib.i64(rows), _lib.i32(d),
+              _lib.f32(LOG2E / hd ** 0.5), ws, st)
     _lib.call("ampconv_attn_fwd_bf16", q, k, v, graph.dst_rowptr, graph.dst_src, graph.inv_deg, None, agg, lse2,
               _lib.i64(n), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(num_heads),
               ws, _lib.size_t(ws.numel() * 4), st)
-    _lib.call("ampconv_out_proj_f32", agg, w_out, b_out, graph.has_in, out,
-              _lib.i64(n), _lib.i32(f), _lib.i32(d), st)
+    _lib.call("ampconv_out_proj_tc", agg, w_out, b_out, graph.has_in, out,
+              _lib.i64(n), _lib.i32(f), _lib.i32(d), ws, st)
     saved = _Saved("bf16", graph, (n, e, f, d, num_heads), None, agg, None, bf16=(q, k, v, lse2, ws),
                    inputs=(x, w_in.detach(), b_in.detach()))
     return out, saved
@@ -155,8 +155,10 @@ def _backward_bf16(saved, x, w_in, w_out, d_out):
     d_w_out = torch.empty_like(w_out)
     d_b_out = torch.empty(d, dtype=torch.float32, device=dev)
     ws = _param_grad_ws(3 * d, d, dev)
-    _lib.call("ampconv_out_proj_bwd_bf16", d_out, saved.agg, w_out, g.inv_deg, g.has_in,
-              d_agg, d_w_out, d_b_out, _lib.i64(n), _lib.i32(f), _lib.i32(d), ws, _lib.size_t(ws.numel()), st)
+    _lib.call("ampconv_out_proj_bwd_input_tc", d_out, w_out, g.inv_deg, d_agg,
+              _lib.i64(n), _lib.i32(f), _lib.i32(d), bws, st)
+    _lib.call("ampconv_out_proj_bwd_params_tc", d_out, saved.agg, g.has_in, d_w_out, d_b_out,
+              _lib.i64(n), _lib.i32(f), _lib.i32(d), ws, _lib.size_t(ws.numel()), bws, st)
     d_qkv = torch.empty((rows, 3 * d), dtype=torch.float32, device=dev)
     delta = torch.empty_like(lse2)
     tail = (_lib.i64(n), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(h), bws, _lib.size_t(bws.numel() * 4), st)
@@ -166,8 +168,9 @@ def _backward_bf16(saved, x, w_in, w_out, d_out):
     d_x = torch.empty_like(x)
     d_w_in = torch.empty_like(w_in)
     d_b_in = torch.empty(3 * d, dtype=torch.float32, device=dev)
-    _lib.call("ampconv_qkv_proj_bwd_f32", x, d_qkv, w_in, d_x, d_w_in, d_b_in,
-              _lib.i64(rows), _lib.i32(d), ws, _lib.size_t(ws.numel()), st)
+    _lib.call("ampconv_qkv_proj_bwd_input_tc", d_qkv, w_in, d_x, _lib.i64(rows), _lib.i32(d), bws, st)
+    _lib.call("ampconv_qkv_proj_bwd_params_tc", x, d_qkv, d_w_in, d_b_in,
+              _lib.i64(rows), _lib.i32(d), ws, _lib.size_t(ws.numel()), bws, st)
     return d_x, d_w_in, d_b_in, d_w_out, d_b_out
 
 
@@ -259,7 +262,6 @@ def profile_stages(x, graph, w_in, b_in, w_out, b_out, num_heads, d_out, mode, r
         st = _stream(dev)
         fwd = _forward_bf16 if mode == "bf16" else _forward_fp32
         out, saved = fwd(x, graph, w_in, b_in, w_out, b_out, num_heads)
-        saved.ensure_fp32_views()
         d_agg = torch.empty((rows, d), dtype=torch.float32, device=dev)
         d_w_out = torch.empty_like(w_out)
         d_b_out = torch.empty(d, dtype=torch.float32, device=dev)
@@ -267,7 +269,6 @@ def profile_stages(x, graph, w_in, b_in, w_out, b_out, num_heads, d_out, mode, r
         _lib.call("ampconv_out_proj_bwd_f32", d_out.contiguous(), saved.agg, w_out, graph.inv_deg, graph.has_in,
                   d_agg, d_w_out, d_b_out, _lib.i64(n), _lib.i32(f), _lib.i32(d), ws, _lib.size_t(ws.numel()), st)
         d_qkv = torch.empty((rows, 3 * d), dtype=torch.float32, device=dev)
-        delta = torch.empty_like(saved.lse)
         dims = (_lib.i64(n), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(num_heads), st)
         calls = {}
         if mode == "bf16":
@@ -279,10 +280,22 @@ def profile_stages(x, graph, w_in, b_in, w_out, b_out, num_heads, d_out, mode, r
         else:
             calls["attn_fwd"] = lambda: _lib.call("ampconv_attn_fwd_f32", saved.qkv, graph.dst_rowptr, graph.dst_src,
                                                   graph.inv_deg, saved.agg, saved.lse, *dims)
-        calls["attn_bwd_dq"] = lambda: _lib.call("ampconv_attn_bwd_dq_f32", saved.qkv, d_agg, saved.lse,
-                                                 graph.dst_rowptr, graph.dst_src, d_qkv, delta, *dims)
-        calls["attn_bwd_dkv"] = lambda: _lib.call("ampconv_attn_bwd_dkv_f32", saved.qkv, d_agg, saved.lse, delta,
-                                                  graph.src_rowptr, graph.src_dst, graph.src_pos, d_qkv, *dims)
+        if mode == "bf16":
+            q, k, v, lse2, bws = saved.bf16
+            d_agg16 = d_agg.to(torch.bfloat16)
+            delta2 = torch.empty_like(lse2)
+            tail = (_lib.i64(n), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(num_heads), bws,
+                    _lib.size_t(bws.numel() * 4), st)
+            calls["attn_bwd_dq"] = lambda: _lib.call("ampconv_attn_bwd_dq_bf16", q, k, v, d_agg16, lse2,
+                                                     graph.dst_rowptr, graph.dst_src, d_qkv, delta2, *tail)
+            calls["attn_bwd_dkv"] = lambda: _lib.call("ampconv_attn_bwd_dkv_bf16", q, k, v, d_agg16, lse2, delta2,
+                                                      graph.src_rowptr, graph.src_dst, graph.src_pos, d_qkv, *tail)
+        else:
+            delta = torch.empty_like(saved.lse)
+            calls["attn_bwd_dq"] = lambda: _lib.call("ampconv_attn_bwd_dq_f32", saved.qkv, d_agg, saved.lse,
+                                                     graph.dst_rowptr, graph.dst_src, d_qkv, delta, *dims)
+            calls["attn_bwd_dkv"] = lambda: _lib.call("ampconv_attn_bwd_dkv_f32", saved.qkv, d_agg, saved.lse, delta,
+                                                      graph.src_rowptr, graph.src_dst, graph.src_pos, d_qkv, *dims)
         result = {}
         for name, fn in calls.items():
             fn()

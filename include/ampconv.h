@@ -174,6 +174,14 @@ AMPCONV_API int ampconv_attn_fwd_bf16(const void* q, const void* k, const void* 
                           int64_t num_nodes, int64_t num_edges, int F, int d, int H,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* Debug variant of ampconv_attn_fwd_bf16: also fills prof[0..10] (device int64) with per-phase cycle counts of
+ * one softmax warp (see csrc/attn_bf16.cu).  Used by tools/phase_profile.py only. */
+AMPCONV_API int ampconv_attn_fwd_bf16_profile(const void* q, const void* k, const void* v,
+                                  const int32_t* dst_rowptr, const int32_t* dst_src, const float* inv_deg,
+                                  const int32_t* order, float* agg, float* lse2,
+                                  int64_t num_nodes, int64_t num_edges, int F, int d, int H,
+                                  void* workspace, size_t workspace_bytes, void* stream, long long* prof);
+
 /* Backward of ampconv_out_proj_f32 for the bf16 family: identical, except that d_agg (already
  * multiplied by inv_deg) is emitted as bf16 [N,F,d], the dO tile the tcgen05 backward kernels load. */
 AMPCONV_API int ampconv_out_proj_bwd_bf16(const float* d_out, const float* agg, const float* out_proj_weight,
@@ -196,6 +204,35 @@ AMPCONV_API int ampconv_attn_bwd_dkv_bf16(const void* q, const void* k, const vo
                               const int32_t* src_dst, const int32_t* src_pos, float* d_qkv,
                               int64_t num_nodes, int64_t num_edges, int F, int d, int H,
                               void* workspace, size_t workspace_bytes, void* stream);
+
+/* tcgen05 node-level projections (d = 64): same contracts as ampconv_qkv_proj_bf16, ampconv_out_proj_f32 and
+ * the input-gradient halves of ampconv_out_proj_bwd_bf16 / ampconv_qkv_proj_bwd_f32, as HBM-bound persistent
+ * kernels (fp32 rows are converted to bf16 on the way into shared memory, fp32 accumulation in TMEM).
+ * `workspace` is the family's >= 256-byte workspace. */
+AMPCONV_API int ampconv_qkv_proj_tc(const float* x, const float* in_proj_weight, const float* in_proj_bias,
+                        void* q, void* k, void* v, int64_t rows, int d, float q_scale, void* workspace, void* stream);
+AMPCONV_API int ampconv_out_proj_tc(const float* agg, const float* out_proj_weight, const float* out_proj_bias,
+                        const float* has_in, float* out, int64_t num_nodes, int F, int d, void* workspace, void* stream);
+AMPCONV_API int ampconv_out_proj_bwd_input_tc(const float* d_out, const float* out_proj_weight, const float* inv_deg,
+                                  void* d_agg_bf16, int64_t num_nodes, int F, int d, void* workspace, void* stream);
+AMPCONV_API int ampconv_qkv_proj_bwd_input_tc(const float* d_qkv, const float* in_proj_weight, float* d_x,
+                                  int64_t rows, int d, void* workspace, void* stream);
+/* Parameter-gradient halves (d_w, d_b) of the two projection backwards; workspace as for the combined calls. */
+AMPCONV_API int ampconv_out_proj_bwd_params_f32(const float* d_out, const float* agg, const float* has_in,
+                                    float* d_w, float* d_b, int64_t num_nodes, int F, int d,
+                                    void* workspace, size_t workspace_bytes, void* stream);
+AMPCONV_API int ampconv_qkv_proj_bwd_params_f32(const float* x, const float* d_qkv, float* d_w, float* d_b,
+                                    int64_t rows, int d, void* workspace, size_t workspace_bytes, void* stream);
+
+/* tcgen05 versions of the two parameter-gradient reductions (d = 64): both operands are MN-major bf16 tiles,
+ * the bias gradient comes out of the same MMA through a gate column; per-CTA partials + deterministic reduce.
+ * scratch: ampconv_param_grad_workspace_bytes(3d, d) bytes; workspace: the family's >= 256-byte workspace. */
+AMPCONV_API int ampconv_out_proj_bwd_params_tc(const float* d_out, const float* agg, const float* has_in,
+                                   float* d_w, float* d_b, int64_t num_nodes, int F, int d,
+                                   void* scratch, size_t scratch_bytes, void* workspace, void* stream);
+AMPCONV_API int ampconv_qkv_proj_bwd_params_tc(const float* x, const float* d_qkv, float* d_w, float* d_b,
+                                   int64_t rows, int d, void* scratch, size_t scratch_bytes, void* workspace,
+                                   void* stream);
 
 /* Copies the status word of the last bf16 kernel that used `workspace` to the host (0 = ok, otherwise
  * the id of the pipeline wait that timed out).  Synchronises `stream`; meant for tests and debugging. */

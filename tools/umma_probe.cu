@@ -4,6 +4,7 @@
 //   mode 2  O = P V_h            SS MMA, A = P in smem (K-major SW128, two 64-column atoms)
 //   mode 3  TMA 3D tensor-map load (box 128 x 64 over an F=100 node): raw smem image vs expected swizzle
 //   mode 4  mode 0 with both tiles brought in by TMA
+//   mode 6  D[128x64] = A^T B    SS MMA, BOTH operands MN-major SW128 (A = two 64-column atoms, LBO = atom stride)
 //   mode 5  MUFU ex2 throughput: f32 vs bf16x2 vs f16x2; fma.rn.f32x2 vs scalar fma
 // Every mbarrier wait is bounded, so a wrong descriptor reports a timeout instead of hanging the GPU.
 // Usage: umma_probe <mode> [h] [lbo_bytes] [sbo_bytes] [b_major_mn]
@@ -50,7 +51,7 @@ probe_kernel(Params p, const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16*
   const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
   bool ok = true;
 
-  if (p.mode == 0 || p.mode == 1 || p.mode == 2) {
+  if (p.mode == 0 || p.mode == 1 || p.mode == 2 || p.mode == 6) {
     // manual swizzled fill: tile rows are 128 B (64 bf16)
     const __nv_bfloat16* srcB = (p.mode == 0) ? K : V;
     for (int idx = tid; idx < 128 * 8; idx += 128) {       // 16-byte chunks
@@ -62,7 +63,7 @@ probe_kernel(Params p, const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16*
         *reinterpret_cast<uint4*>(sA + sw128_offset(row, chunk * 16)) = va;
       }
     }
-    if (p.mode == 2) {
+    if (p.mode == 2 || p.mode == 6) {
       for (int idx = tid; idx < 128 * 16; idx += 128) {    // P is 128 x 128: two atoms of 64 columns
         int row = idx >> 4, chunk = idx & 15;
         uint4 va = *reinterpret_cast<const uint4*>(P + row * 128 + chunk * 8);
@@ -111,6 +112,12 @@ probe_kernel(Params p, const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16*
           uint64_t db = smem_desc(smem_u32(sB) + s * 2048 + p.h * 32, p.lbo, p.sbo, LAYOUT_SW128);
           mma_ts(tmem + 256, tmem + 128 + 8 * s, db, idesc_bf16(128, 16, 0, p.b_mn), s > 0);
         }
+      } else if (p.mode == 6) {
+        for (int s = 0; s < 8; ++s) {
+          uint64_t da = smem_desc(smem_u32(sA) + s * 2048, p.lbo, p.sbo, LAYOUT_SW128);
+          uint64_t db = smem_desc(smem_u32(sB) + s * 2048, 16, 1024, LAYOUT_SW128);
+          mma_ss(tmem + 256, da, db, idesc_bf16(128, 64, 1, 1), s > 0);
+        }
       } else {  // mode 2
         for (int s = 0; s < 8; ++s) {
           uint64_t da = smem_desc(smem_u32(sA) + (s >> 2) * 16384 + (s & 3) * 32, 16, 1024, LAYOUT_SW128);
@@ -132,6 +139,14 @@ probe_kernel(Params p, const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16*
           tmem_ld_wait();
 #pragma unroll
           for (int c = 0; c < 32; ++c) out[row * 128 + c0 + c] = __uint_as_float(r[c]);
+        }
+      } else if (p.mode == 6) {
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(lane_addr + 256 + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) out[row * 64 + c0 + c] = __uint_as_float(r[c]);
         }
       } else {
         uint32_t r[16];
@@ -285,6 +300,14 @@ int main(int argc, char** argv) {
         double s = 0;
         for (int j = 0; j < 128; ++j) s += (double)hp[i * 128 + j] * hv[j * 64 + 16 * p.h + c];
         max_err = fmax(max_err, fabs(s - ho[i * 16 + c]));
+        max_ref = fmax(max_ref, fabs(s));
+      }
+  } else if (p.mode == 6) {
+    for (int m = 0; m < 128; ++m)
+      for (int n = 0; n < 64; ++n) {
+        double s = 0;
+        for (int k = 0; k < 128; ++k) s += (double)hp[k * 128 + m] * hv[k * 64 + n];
+        max_err = fmax(max_err, fabs(s - ho[m * 64 + n]));
         max_ref = fmax(max_ref, fabs(s));
       }
   } else if (p.mode == 3) {
