@@ -178,26 +178,30 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
     // Two cursors over the global item sequence (item = edge * H + head): the score MMAs run ahead as far as
     // the S buffers allow, the P V MMAs follow as soon as a warpgroup has published P.  Every wait of the
     // score cursor keeps servicing the P V cursor, so neither can starve the other.
-    if (lane == 0) {
+    {
       const uint32_t idesc_qk = idesc_bf16(128, nqk, 0, 0);
       const uint32_t idesc_pv = idesc_bf16(128, HD, 0, 1);
       uint32_t qi = 0, g_qk = 0, g_pv = 0;
+      const bool mprof = PROF && blockIdx.x == 0;
+      long long mt_pv = 0, mt_qk = 0, mt_start = mprof ? clock64() : 0;
       auto service_pv = [&]() -> bool {
         if (g_pv >= g_qk) return false;
         const uint32_t h = g_pv % H, edge = g_pv / H, b = h & 1;
         const uint32_t cc = edge * HL + (h >> 1), ob = cc & 1, st = edge % kStages;
         if (!mbar_test_wait(&sm.p_full[b], cc & 1)) return false;
         if (!mbar_test_wait(&sm.o_empty[b][ob], ((cc >> 1) & 1) ^ 1)) return false;
+        const long long t0 = mprof ? clock64() : 0;
         tc_fence_after();
         const uint32_t v_base = smem_u32(sm.kv[st][1]) + h * (HD * 2);
         const uint32_t o_col = tmem + 384 + (2 * b + ob) * HD;
         const uint32_t p_col = tmem + 256 + b * 64;
         for (int ks = 0; ks < ksteps; ++ks)
-          mma_ts(o_col, p_col + 8 * ks, smem_desc(v_base + ks * 2048, 16, 1024, LAYOUT_SW128), idesc_pv, ks > 0);
-        mma_commit(&sm.o_full[b][ob]);
-        mma_commit(&sm.p_empty[b]);
-        if (h == H - 1) mma_commit(&sm.kv_empty[st]);
+          mma_ts_w(o_col, p_col + 8 * ks, smem_desc(v_base + ks * 2048, 16, 1024, LAYOUT_SW128), idesc_pv, ks > 0);
+        mma_commit_w(&sm.o_full[b][ob]);
+        mma_commit_w(&sm.p_empty[b]);
+        if (h == H - 1) mma_commit_w(&sm.kv_empty[st]);
         ++g_pv;
+        if (mprof) mt_pv += clock64() - t0;
         return true;
       };
       auto wait_serving = [&](uint64_t* bar, uint32_t parity) -> bool {
@@ -218,7 +222,6 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
         if (!wait_serving(&sm.q_full[qb], (qi >> 1) & 1)) AMP_FAIL(201);
         const NodeSlot ns = sm.slot[qb];
         if (ns.node < 0) break;
-        if (ns.p_end == ns.p_begin) mbar_arrive(&sm.q_empty[qb]);
         for (int p = ns.p_begin; p < ns.p_end; ++p) {
           const uint32_t edge = g_qk / H, st = edge % kStages;
           if (!wait_serving(&sm.kv_full[st], (edge / kStages) & 1)) AMP_FAIL(202);
@@ -227,16 +230,18 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
             const uint32_t b = h & 1;
             const uint32_t cc = edge * HL + (h >> 1);
             if (!wait_serving(&sm.s_empty[b], (cc & 1) ^ 1)) AMP_FAIL(203);
+            const long long t0 = mprof ? clock64() : 0;
             tc_fence_after();
             const uint32_t qa = smem_u32(sm.q[qb]) + h * (HD * 2);
             const uint32_t ka = smem_u32(sm.kv[st][0]) + h * (HD * 2);
 #pragma unroll
             for (int ks = 0; ks < HD / 16; ++ks)
-              mma_ss(tmem + b * 128, smem_desc(qa + ks * 32, 16, 1024, LAYOUT_SW128),
+              mma_ss_w(tmem + b * 128, smem_desc(qa + ks * 32, 16, 1024, LAYOUT_SW128),
                      smem_desc(ka + ks * 32, 16, 1024, LAYOUT_SW128), idesc_qk, ks > 0);
-            mma_commit(&sm.s_full[b]);
-            if (p + 1 == ns.p_end && h == H - 1) mma_commit(&sm.q_empty[qb]);
+            mma_commit_w(&sm.s_full[b]);
+            if (p + 1 == ns.p_end && h == H - 1) mma_commit_w(&sm.q_empty[qb]);
             ++g_qk;
+            if (mprof) mt_qk += clock64() - t0;
             service_pv();
           }
         }
@@ -248,6 +253,12 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
           if (service_pv()) { t0 = global_timer_ns(); continue; }
           if (global_timer_ns() - t0 > 250000000ull) AMP_FAIL(205);
         }
+      }
+      if (mprof && lane == 0) {
+        prof[12] = clock64() - mt_start;   // MMA thread: total, issuing score MMAs, issuing P V MMAs, items
+        prof[13] = mt_qk;
+        prof[14] = mt_pv;
+        prof[15] = g_qk;
       }
     }
   } else {

@@ -192,7 +192,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
     // ------------------------------------------------------------------ MMA issuer
     // Two cursors over the global item sequence (item = edge * H + head): X/Y score MMAs and the T MMAs that
     // consume the bf16 operands a warpgroup wrote back.  Waits of the first cursor keep servicing the second.
-    if (lane == 0) {
+    {
       const uint32_t idesc_xy = idesc_bf16(128, nqk, 0, 0);
       const uint32_t idesc_t = idesc_bf16(128, HD, 0, 1);
       uint32_t qi = 0, g_xy = 0, g_t = 0;
@@ -207,11 +207,11 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
         const uint32_t btx = smem_u32(sm.edge[st][MODE == MODE_DQ ? 0 : 1]) + h * (HD * 2);
         const uint32_t bty = smem_u32(sm.edge[st][0]) + h * (HD * 2);
         for (int ks = 0; ks < ksteps; ++ks)
-          mma_ts(x_col + 64, x_col + 8 * ks, smem_desc(btx + ks * 2048, 16, 1024, LAYOUT_SW128), idesc_t, ks > 0);
+          mma_ts_w(x_col + 64, x_col + 8 * ks, smem_desc(btx + ks * 2048, 16, 1024, LAYOUT_SW128), idesc_t, ks > 0);
         for (int ks = 0; ks < ksteps; ++ks)
-          mma_ts(y_col + 64, y_col + 8 * ks, smem_desc(bty + ks * 2048, 16, 1024, LAYOUT_SW128), idesc_t, ks > 0);
-        mma_commit(&sm.t_full[b]);
-        if (h == H - 1) mma_commit(&sm.edge_empty[st]);
+          mma_ts_w(y_col + 64, y_col + 8 * ks, smem_desc(bty + ks * 2048, 16, 1024, LAYOUT_SW128), idesc_t, ks > 0);
+        mma_commit_w(&sm.t_full[b]);
+        if (h == H - 1) mma_commit_w(&sm.edge_empty[st]);
         ++g_t;
         return true;
       };
@@ -247,14 +247,14 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
             const uint32_t b0 = smem_u32(sm.edge[st][0]) + hb, b1 = smem_u32(sm.edge[st][1]) + hb;
 #pragma unroll
             for (int ks = 0; ks < HD / 16; ++ks)
-              mma_ss(tmem + b * 256, smem_desc(a0 + ks * 32, 16, 1024, LAYOUT_SW128),
+              mma_ss_w(tmem + b * 256, smem_desc(a0 + ks * 32, 16, 1024, LAYOUT_SW128),
                      smem_desc(b0 + ks * 32, 16, 1024, LAYOUT_SW128), idesc_xy, ks > 0);
 #pragma unroll
             for (int ks = 0; ks < HD / 16; ++ks)
-              mma_ss(tmem + b * 256 + 128, smem_desc(a1 + ks * 32, 16, 1024, LAYOUT_SW128),
+              mma_ss_w(tmem + b * 256 + 128, smem_desc(a1 + ks * 32, 16, 1024, LAYOUT_SW128),
                      smem_desc(b1 + ks * 32, 16, 1024, LAYOUT_SW128), idesc_xy, ks > 0);
-            mma_commit(&sm.xy_full[b]);
-            if (e + 1 == ns.e_end && h == H - 1) mma_commit(&sm.own_empty[qb]);
+            mma_commit_w(&sm.xy_full[b]);
+            if (e + 1 == ns.e_end && h == H - 1) mma_commit_w(&sm.own_empty[qb]);
             ++g_xy;
             service_t();
           }

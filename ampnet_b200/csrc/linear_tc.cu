@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearArgs
     }
   } else if (warp == 4) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    {
       const uint32_t idesc = idesc_bf16(128, N, 0, 0);
       uint32_t it = 0;
       for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -139,10 +139,10 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearArgs
         for (int ka = 0; ka < K / 64; ++ka)
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            mma_ss(tmem + buf * 256, smem_desc(smem_u32(sm.a[st][ka]) + ks * 32, 16, 1024, LAYOUT_SW128),
+            mma_ss_w(tmem + buf * 256, smem_desc(smem_u32(sm.a[st][ka]) + ks * 32, 16, 1024, LAYOUT_SW128),
                    smem_desc(smem_u32(sm.b[ka]) + ks * 32, 16, 1024, LAYOUT_SW128), idesc, (ka | ks) != 0);
-        mma_commit(&sm.a_empty[st]);
-        mma_commit(&sm.d_full[buf]);
+        mma_commit_w(&sm.a_empty[st]);
+        mma_commit_w(&sm.d_full[buf]);
       }
     }
   } else {

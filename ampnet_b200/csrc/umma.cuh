@@ -178,6 +178,22 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// Converged-warp variants: called by ALL 32 lanes of the issuing warp with warp-uniform arguments; one elected
+// lane executes the instruction.  Keeping the warp converged lets the compiler hold descriptors in uniform
+// registers; issuing from a divergent single-lane region costs a register-to-uniform broadcast loop per MMA.
+__device__ __forceinline__ void mma_ss_w(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if (elect_one()) mma_ss(tmem_d, desc_a, desc_b, idesc, accumulate);
+  __syncwarp();
+}
+__device__ __forceinline__ void mma_ts_w(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if (elect_one()) mma_ts(tmem_d, tmem_a, desc_b, idesc, accumulate);
+  __syncwarp();
+}
+__device__ __forceinline__ void mma_commit_w(uint64_t* bar) {
+  if (elect_one()) mma_commit(bar);
+  __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------
 // TMEM <-> registers.  32x32b shape: thread t of warp w touches lane 32*(w%4)+t, consecutive columns.
 // ------------------------------------------------------------------------------------------

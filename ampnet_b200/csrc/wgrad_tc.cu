@@ -169,7 +169,7 @@ wgrad_tc_kernel(const float* __restrict__ A, const float* __restrict__ B, const 
     }
   } else if (warp == 4) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    {
       const uint32_t idesc = idesc_bf16(128, NB, 1, 1);
       // M = 128 gradient columns per MMA = two 64-column atoms 16 KB apart.  Where the second atom does not exist
       // (MW == 64, or the v block of MW == 192) the MMA reads whatever shared memory follows; every accumulator row
@@ -184,15 +184,15 @@ wgrad_tc_kernel(const float* __restrict__ A, const float* __restrict__ B, const 
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
           const uint64_t db = smem_desc(smem_u32(sm.b[st][0]) + ks * 2048, kAtomBytes, 1024, LAYOUT_SW128);
-          mma_ss(tmem, smem_desc(smem_u32(sm.a[st][0]) + ks * 2048, lbo_a01, 1024, LAYOUT_SW128), db, idesc,
+          mma_ss_w(tmem, smem_desc(smem_u32(sm.a[st][0]) + ks * 2048, lbo_a01, 1024, LAYOUT_SW128), db, idesc,
                  (it | ks) != 0);
           if (MW == 192)
-            mma_ss(tmem + 96, smem_desc(smem_u32(sm.a[st][2]) + ks * 2048, lbo_a01, 1024, LAYOUT_SW128), db, idesc,
+            mma_ss_w(tmem + 96, smem_desc(smem_u32(sm.a[st][2]) + ks * 2048, lbo_a01, 1024, LAYOUT_SW128), db, idesc,
                    (it | ks) != 0);
         }
-        mma_commit(&sm.empty[st]);
+        mma_commit_w(&sm.empty[st]);
       }
-      if (ok) mma_commit(&sm.done);
+      if (ok) mma_commit_w(&sm.done);
     }
   }
   tc_fence_before();

@@ -32,6 +32,9 @@ def main():
     print(f"items={items} total cycles/item={tot / items:.0f}")
     for nm, c in zip(names, p[:10]):
         print(f"  {nm:18s} {c / items:8.1f} cyc/item  {100.0 * c / tot:5.1f}%")
+    mi = max(1, p[15])
+    print(f"MMA thread: items={mi} total/item={p[12] / mi:.0f} issue-QK/item={p[13] / mi:.0f} issue-PV/item={p[14] / mi:.0f} "
+          f"idle/item={(p[12] - p[13] - p[14]) / mi:.0f}")
 
 if __name__ == "__main__":
     main()

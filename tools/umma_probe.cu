@@ -5,6 +5,7 @@
 //   mode 3  TMA 3D tensor-map load (box 128 x 64 over an F=100 node): raw smem image vs expected swizzle
 //   mode 4  mode 0 with both tiles brought in by TMA
 //   mode 6  D[128x64] = A^T B    SS MMA, BOTH operands MN-major SW128 (A = two 64-column atoms, LBO = atom stride)
+//   mode 7  MMA issue/completion cost: 256 back-to-back TS (h=0) or SS (h=1) MMAs, N = lbo arg, #accumulators = sbo arg
 //   mode 5  MUFU ex2 throughput: f32 vs bf16x2 vs f16x2; fma.rn.f32x2 vs scalar fma
 // Every mbarrier wait is bounded, so a wrong descriptor reports a timeout instead of hanging the GPU.
 // Usage: umma_probe <mode> [h] [lbo_bytes] [sbo_bytes] [b_major_mn]
@@ -213,6 +214,43 @@ static int run_pipe(const char* name, int elems_per_iter) {
   return 0;
 }
 
+__global__ void __launch_bounds__(128)
+mma_cost_kernel(int use_ss, int N, int nacc, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 49152 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (warp == 1) {
+    const uint32_t idesc = idesc_bf16(128, N, 0, use_ss ? 0 : 1);
+    const long long t0 = clock64();
+    for (int i = 0; i < 256; ++i) {
+      const uint32_t d = tmem + 256 + (i % nacc) * (N < 32 ? 32 : N);
+      if (use_ss)
+        mma_ss_w(d, smem_desc(smem_u32(smem) + (i & 3) * 32, 16, 1024, LAYOUT_SW128),
+                 smem_desc(smem_u32(smem + 16384) + (i & 3) * 32, 16, 1024, LAYOUT_SW128), idesc, 1);
+      else
+        mma_ts_w(d, tmem + 8 * (i & 7), smem_desc(smem_u32(smem + 16384) + (i & 7) * 2048, 16, 1024, LAYOUT_SW128), idesc, 1);
+    }
+    const long long t1 = clock64();
+    mma_commit_w(&bar);
+    mbar_wait(&bar, 0);
+    const long long t2 = clock64();
+    if (tid == 32) { out[0] = t1 - t0; out[1] = t2 - t0; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 static float bf(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
 int main(int argc, char** argv) {
@@ -223,6 +261,19 @@ int main(int argc, char** argv) {
   if (argc > 4) p.sbo = atoi(argv[4]);
   if (argc > 5) p.b_mn = atoi(argv[5]);
   printf("mode=%d h=%d lbo=%d sbo=%d b_mn=%d\n", p.mode, p.h, p.lbo, p.sbo, p.b_mn);
+  if (p.mode == 7) {
+    long long* dout;
+    CK(cudaMalloc(&dout, 16));
+    const size_t smem = 49152 + 1024;
+    CK(cudaFuncSetAttribute(mma_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int rep = 0; rep < 2; ++rep) mma_cost_kernel<<<1, 128, smem>>>(p.h, p.lbo, p.sbo, dout);
+    CK(cudaDeviceSynchronize());
+    long long h[2];
+    CK(cudaMemcpy(h, dout, 16, cudaMemcpyDeviceToHost));
+    printf("RESULT mode=7 %s N=%d accumulators=%d: issue %.1f clk/MMA, issue+complete %.1f clk/MMA\n", p.h ? "SS" : "TS",
+           p.lbo, p.sbo, h[0] / 256.0, h[1] / 256.0);
+    return 0;
+  }
   if (p.mode == 5) {
     run_pipe<0>("ex2.f32", 4);
     run_pipe<1>("ex2.bf16x2", 8);
