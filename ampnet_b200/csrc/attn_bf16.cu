@@ -8,14 +8,16 @@
 //   producer warp : dynamic node scheduler + TMA (cp.async.bulk.tensor, 128B swizzle) of the
 //                   destination's Q tile (once per node) and each in-edge's K and V tiles
 //                   ("gather by edge index" = a TMA box at row src*F of the node-major tensors);
-//   MMA warp      : one elected thread issues tcgen05.mma:  S_h = Q_h K_h^T  (SS, K-major operands,
-//                   head = 32-byte slice of the 128-byte swizzled row) into TMEM and
-//                   O_h = P_h V_h (TS: P read from TMEM, V as MN-major operand straight from the
-//                   row-major tile);
+//   3 MMA warps   : tcgen05.mma is issued by one elected lane of a converged warp.  Warp 9 issues the
+//                   scores S_h = Q_h K_h^T (SS, K-major operands, head = 32-byte slice of the 128-byte
+//                   swizzled row); warps 10 / 11 issue O_h += P_h V_h for the heads of softmax
+//                   warpgroup 0 / 1 (TS: P read from TMEM, V as MN-major operand straight from the
+//                   row-major tile).  Issue cost (~100 clk per tcgen05 op) is what the split hides;
 //   2 softmax warpgroups: thread = one destination token (TMEM lane); row max / exp2 / row sum in
-//                   registers, P written back to TMEM as bf16, per-edge normalised O accumulated in
-//                   registers over all in-edges of the destination (the mean aggregation: no
-//                   atomics, no [E,F,d] message tensor, no [E,H,F,F] probabilities in HBM).
+//                   registers, the NORMALISED probabilities written back to TMEM as bf16, so that the
+//                   P V MMAs of all in-edges of the destination accumulate straight into one TMEM
+//                   tile (the mean aggregation: no atomics, no per-edge read-back, no [E,F,d]
+//                   message tensor, no [E,H,F,F] probabilities in HBM).
 //
 // Layouts: Q', K, V are bf16 [N, F, 64] node-major, rows of 128 bytes; Q' is pre-multiplied by
 // log2(e)/sqrt(hd) so that scores are in the log2 domain.  lse2[p,h,i] = max + log2(sum) per
@@ -33,8 +35,8 @@ using namespace umma;
 
 constexpr int kD = 64;                 // embed dim of this kernel family (one 128-byte swizzle atom per row)
 constexpr int kTileBytes = 128 * 128;  // 128 tokens x 64 bf16
-constexpr int kStages = 4;             // K/V ring depth
-constexpr int kFwdThreads = 320;       // 2 softmax warpgroups + producer warp + MMA warp
+constexpr int kStages = 5;             // K/V ring depth
+constexpr int kFwdThreads = 384;       // 2 softmax warpgroups + producer warp + 3 MMA-issuing warps
 
 struct NodeSlot {
   int node, p_begin, p_end;
@@ -48,10 +50,9 @@ struct FwdSmem {
   uint64_t q_full[2], q_empty[2];
   uint64_t kv_full[kStages], kv_empty[kStages];
   uint64_t s_full[2], s_empty[2], p_full[2], p_empty[2];
-  uint64_t o_full[2][2], o_empty[2][2];
+  uint64_t o_full[2], o_empty[2];     // per node parity: O tile complete / read back
   NodeSlot slot[2];
   uint32_t tmem_base;
-  float acc[32][256];   // per-thread output accumulators [heads-per-warpgroup * HD][softmax thread]
 };
 
 // first failure wins: status = code | blockIdx << 16
@@ -83,19 +84,17 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sm.q_full[i], 1);
-      mbar_init(&sm.q_empty[i], 1 + 8);
+      mbar_init(&sm.q_empty[i], 1 + 8 + 2);
       mbar_init(&sm.s_full[i], 1);
       mbar_init(&sm.s_empty[i], 4);
       mbar_init(&sm.p_full[i], 4);
       mbar_init(&sm.p_empty[i], 1);
-      for (int j = 0; j < 2; ++j) {
-        mbar_init(&sm.o_full[i][j], 1);
-        mbar_init(&sm.o_empty[i][j], 4);
-      }
+      mbar_init(&sm.o_full[i], 2);
+      mbar_init(&sm.o_empty[i], 8);
     }
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&sm.kv_full[i], 1);
-      mbar_init(&sm.kv_empty[i], 1);
+      mbar_init(&sm.kv_empty[i], 3);
     }
     fence_barrier_init();
   }
@@ -108,7 +107,7 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
-  // TMEM columns: S[b] = b*128 (fp32 scores), P[b] = 256 + b*64 (bf16 pairs), O[b][ob] = 384 + (2b+ob)*HD
+  // TMEM columns: S[b] = b*128 (fp32 scores), P[b] = 256 + b*64 (bf16 pairs), O[node parity] = 384 + 64*par + h*HD
   const int nqk = ((F + 15) >> 4) << 4;   // MMA N of the score tile
   const int ksteps = (F + 15) >> 4;       // K steps of P V
 
@@ -174,91 +173,71 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       if (node < 0) break;
     }
   } else if (warp == 9) {
-    // ------------------------------------------------------------------ MMA issuer
-    // Two cursors over the global item sequence (item = edge * H + head): the score MMAs run ahead as far as
-    // the S buffers allow, the P V MMAs follow as soon as a warpgroup has published P.  Every wait of the
-    // score cursor keeps servicing the P V cursor, so neither can starve the other.
+    // ------------------------------------------------------------------ score MMAs (all heads)
     {
       const uint32_t idesc_qk = idesc_bf16(128, nqk, 0, 0);
-      const uint32_t idesc_pv = idesc_bf16(128, HD, 0, 1);
-      uint32_t qi = 0, g_qk = 0, g_pv = 0;
-      const bool mprof = PROF && blockIdx.x == 0;
-      long long mt_pv = 0, mt_qk = 0, mt_start = mprof ? clock64() : 0;
-      auto service_pv = [&]() -> bool {
-        if (g_pv >= g_qk) return false;
-        const uint32_t h = g_pv % H, edge = g_pv / H, b = h & 1;
-        const uint32_t cc = edge * HL + (h >> 1), ob = cc & 1, st = edge % kStages;
-        if (!mbar_test_wait(&sm.p_full[b], cc & 1)) return false;
-        if (!mbar_test_wait(&sm.o_empty[b][ob], ((cc >> 1) & 1) ^ 1)) return false;
-        const long long t0 = mprof ? clock64() : 0;
-        tc_fence_after();
-        const uint32_t v_base = smem_u32(sm.kv[st][1]) + h * (HD * 2);
-        const uint32_t o_col = tmem + 384 + (2 * b + ob) * HD;
-        const uint32_t p_col = tmem + 256 + b * 64;
-        for (int ks = 0; ks < ksteps; ++ks)
-          mma_ts_w(o_col, p_col + 8 * ks, smem_desc(v_base + ks * 2048, 16, 1024, LAYOUT_SW128), idesc_pv, ks > 0);
-        mma_commit_w(&sm.o_full[b][ob]);
-        mma_commit_w(&sm.p_empty[b]);
-        if (h == H - 1) mma_commit_w(&sm.kv_empty[st]);
-        ++g_pv;
-        if (mprof) mt_pv += clock64() - t0;
-        return true;
-      };
-      auto wait_serving = [&](uint64_t* bar, uint32_t parity) -> bool {
-        uint64_t t0 = 0;
-        for (uint32_t spins = 0;; ++spins) {
-          if (mbar_test_wait(bar, parity)) return true;
-          if (service_pv()) { t0 = 0; continue; }
-          __nanosleep(20);
-          if ((spins & 255) == 255) {
-            const uint64_t now = global_timer_ns();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 250000000ull) return false;
-          }
-        }
-      };
-      for (;;) {
+      uint32_t qi = 0, edge = 0;
+      for (;; ++qi) {
         const uint32_t qb = qi & 1;
-        if (!wait_serving(&sm.q_full[qb], (qi >> 1) & 1)) AMP_FAIL(201);
+        AMP_WAIT(&sm.q_full[qb], (qi >> 1) & 1, 201);
         const NodeSlot ns = sm.slot[qb];
         if (ns.node < 0) break;
-        for (int p = ns.p_begin; p < ns.p_end; ++p) {
-          const uint32_t edge = g_qk / H, st = edge % kStages;
-          if (!wait_serving(&sm.kv_full[st], (edge / kStages) & 1)) AMP_FAIL(202);
+        for (int p = ns.p_begin; p < ns.p_end; ++p, ++edge) {
+          const uint32_t st = edge % kStages;
+          AMP_WAIT(&sm.kv_full[st], (edge / kStages) & 1, 202);
 #pragma unroll
           for (int h = 0; h < H; ++h) {
             const uint32_t b = h & 1;
             const uint32_t cc = edge * HL + (h >> 1);
-            if (!wait_serving(&sm.s_empty[b], (cc & 1) ^ 1)) AMP_FAIL(203);
-            const long long t0 = mprof ? clock64() : 0;
+            AMP_WAIT(&sm.s_empty[b], (cc & 1) ^ 1, 203);
             tc_fence_after();
-            const uint32_t qa = smem_u32(sm.q[qb]) + h * (HD * 2);
-            const uint32_t ka = smem_u32(sm.kv[st][0]) + h * (HD * 2);
+            const uint64_t qd = smem_desc(smem_u32(sm.q[qb]) + h * (HD * 2), 16, 1024, LAYOUT_SW128);
+            const uint64_t kd = smem_desc(smem_u32(sm.kv[st][0]) + h * (HD * 2), 16, 1024, LAYOUT_SW128);
 #pragma unroll
             for (int ks = 0; ks < HD / 16; ++ks)
-              mma_ss_w(tmem + b * 128, smem_desc(qa + ks * 32, 16, 1024, LAYOUT_SW128),
-                     smem_desc(ka + ks * 32, 16, 1024, LAYOUT_SW128), idesc_qk, ks > 0);
+              mma_ss_w(tmem + b * 128, desc_advance(qd, ks * 32), desc_advance(kd, ks * 32), idesc_qk, ks > 0);
             mma_commit_w(&sm.s_full[b]);
-            if (p + 1 == ns.p_end && h == H - 1) mma_commit_w(&sm.q_empty[qb]);
-            ++g_qk;
-            if (mprof) mt_qk += clock64() - t0;
-            service_pv();
           }
-        }
-        ++qi;
-      }
-      {
-        uint64_t t0 = global_timer_ns();
-        while (g_pv < g_qk) {
-          if (service_pv()) { t0 = global_timer_ns(); continue; }
-          if (global_timer_ns() - t0 > 250000000ull) AMP_FAIL(205);
+          mma_commit_w(&sm.kv_empty[st]);                       // K tile consumed (1 of 3 arrivals)
+          if (p + 1 == ns.p_end) mma_commit_w(&sm.q_empty[qb]);  // Q tile consumed
         }
       }
-      if (mprof && lane == 0) {
-        prof[12] = clock64() - mt_start;   // MMA thread: total, issuing score MMAs, issuing P V MMAs, items
-        prof[13] = mt_qk;
-        prof[14] = mt_pv;
-        prof[15] = g_qk;
+    }
+  } else if (warp >= 10) {
+    // ------------------------------------------------------------------ P V MMAs for softmax warpgroup b = warp - 10
+    {
+      const uint32_t b = warp - 10;
+      const uint32_t idesc_pv = idesc_bf16(128, HD, 0, 1);
+      uint32_t qi = 0, edge = 0, c = 0;
+      for (;; ++qi) {
+        const uint32_t qb = qi & 1;
+        AMP_WAIT(&sm.q_full[qb], (qi >> 1) & 1, 211);
+        const NodeSlot ns = sm.slot[qb];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.q_empty[qb]);
+        if (ns.node < 0) break;
+        const uint32_t par = qi & 1;
+        // the first P V of this node overwrites the O tile of node qi - 2: wait until it has been read back
+        AMP_WAIT(&sm.o_empty[par], ((qi >> 1) & 1) ^ 1, 212);
+        for (int p = ns.p_begin; p < ns.p_end; ++p, ++edge) {
+          const uint32_t st = edge % kStages;
+          const uint32_t keep = p != ns.p_begin;                 // accumulate over the node's edges
+#pragma unroll
+          for (int hl = 0; hl < HL; ++hl, ++c) {
+            const int h = 2 * hl + b;
+            AMP_WAIT(&sm.p_full[b], c & 1, 213);
+            tc_fence_after();
+            const uint64_t vdesc = smem_desc(smem_u32(sm.kv[st][1]) + h * (HD * 2), 16, 1024, LAYOUT_SW128);
+            const uint32_t o_col = tmem + 384 + par * 64 + h * HD;
+            const uint32_t p_col = tmem + 256 + b * 64;
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              if (ks < ksteps) mma_ts_w(o_col, p_col + 8 * ks, desc_advance(vdesc, ks * 2048), idesc_pv, ks > 0 ? 1u : keep);
+            mma_commit_w(&sm.p_empty[b]);
+          }
+          mma_commit_w(&sm.kv_empty[st]);                         // V tile consumed by this warp's heads
+        }
+        mma_commit_w(&sm.o_full[par]);                            // this warp's heads of the node are complete
       }
     }
   } else {
@@ -268,7 +247,6 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
     const bool row_ok = row < F;
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t qi = 0, c = 0;
-    float* acc = &sm.acc[0][b * 128 + row];   // element x of this thread: acc[x * 256]
     // optional phase timers (debug entry point only): cycles spent by warp 0 of CTA 0 in each phase
     const bool do_prof = PROF && blockIdx.x == 0;
     long long pt[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -282,33 +260,6 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.q_empty[qb]);   // slot contents are in registers (8 of the 9 arrivals)
       if (ns.node < 0) break;
-#pragma unroll
-      for (int x = 0; x < HL * HD; ++x) acc[x * 256] = 0.f;
-      float l_prev = 1.f;
-      uint32_t t = 0;
-      // adds O / l of this warpgroup's item `cc` into the accumulators of local head hl_prev
-      auto consume = [&](uint32_t cc, int hl_prev, float l) -> bool {
-        const uint32_t ob = cc & 1;
-        if (!mbar_wait(&sm.o_full[b][ob], (cc >> 1) & 1)) return false;
-        tc_fence_after();
-        AMP_PHASE(6);
-        uint32_t o[HD];
-        if constexpr (HD == 16) {
-          tmem_ld_32x32b_x16(lane_base + 384 + (2 * b + ob) * HD, o);
-        } else {
-          tmem_ld_32x32b_x32(lane_base + 384 + (2 * b + ob) * HD, o);
-        }
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.o_empty[b][ob]);
-        const float inv_l = 1.0f / l;
-        float* a = acc + hl_prev * HD * 256;
-#pragma unroll
-        for (int x = 0; x < HD; ++x) a[x * 256] = fmaf(__uint_as_float(o[x]), inv_l, a[x * 256]);
-        AMP_PHASE(7);
-        return true;
-      };
       for (int p = ns.p_begin; p < ns.p_end; ++p) {
 #pragma unroll
         for (int hl = 0; hl < HL; ++hl) {
@@ -341,52 +292,67 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
           const float m = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])),
                                 fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
           AMP_PHASE(2);
+          float l0 = 0.f, l1 = 0.f;
+          uint32_t pk[64];
+#pragma unroll
+          for (int j = 0; j < 64; ++j) {
+            const float e0 = ex2_approx(__uint_as_float(s[2 * j]) - m);
+            const float e1 = ex2_approx(__uint_as_float(s[2 * j + 1]) - m);
+            l0 += e0;
+            l1 += e1;
+            pk[j] = pack_bf16x2(e0, e1);
+          }
+          const float l = l0 + l1;
+          // normalise in bf16x2 so that the P V MMAs of all in-edges can accumulate into one TMEM tile
+          const float inv_l = 1.0f / l;
+          const uint32_t inv2 = pack_bf16x2(inv_l, inv_l);
+#pragma unroll
+          for (int j = 0; j < 64; ++j) pk[j] = mul_bf16x2(pk[j], inv2);
+          AMP_PHASE(4);
           AMP_WAIT(&sm.p_empty[b], (c & 1) ^ 1, 303);
           AMP_PHASE(3);
           tc_fence_after();
-          float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            uint32_t pk[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float e0 = ex2_approx(__uint_as_float(s[32 * k + 2 * j]) - m);
-              const float e1 = ex2_approx(__uint_as_float(s[32 * k + 2 * j + 1]) - m);
-              l0 += e0;
-              l1 += e1;
-              pk[j] = pack_bf16x2(e0, e1);
-            }
-            tmem_st_32x32b_x16(lane_base + 256 + b * 64 + 16 * k, pk);
-          }
-          const float l = l0 + l1;
-          AMP_PHASE(4);
+          for (int k = 0; k < 4; ++k)
+            tmem_st_32x32b_x16(lane_base + 256 + b * 64 + 16 * k, *reinterpret_cast<uint32_t(*)[16]>(&pk[16 * k]));
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&sm.p_full[b]);
           if (row_ok) lse2[((int64_t)p * H + h) * ((F + 3) & ~3) + row] = m + __log2f(l);
           AMP_PHASE(5);
-          if (t > 0) {
-            if (!consume(c - 1, (hl + HL - 1) % HL, l_prev)) AMP_FAIL(304);
-          }
-          l_prev = l;
           ++c;
-          ++t;
         }
       }
-      if (t > 0) {
-        if (!consume(c - 1, HL - 1, l_prev)) AMP_FAIL(305);
-      }
-      if (row_ok) {
-        float* o = agg + ((int64_t)ns.node * F + row) * kD;
+      // node epilogue: all P V MMAs of the node have landed in O[parity]; read this warpgroup's heads
+      {
+        const uint32_t par = qi & 1;
+        AMP_WAIT(&sm.o_full[par], (qi >> 1) & 1, 304);
+        AMP_PHASE(6);
+        tc_fence_after();
+        uint32_t o[HL][HD];
 #pragma unroll
         for (int hl = 0; hl < HL; ++hl) {
-          float4* o4 = reinterpret_cast<float4*>(o + (2 * hl + b) * HD);
-          const float* a = acc + hl * HD * 256;
+          if constexpr (HD == 16) {
+            tmem_ld_32x32b_x16(lane_base + 384 + par * 64 + (2 * hl + b) * HD, o[hl]);
+          } else {
+            tmem_ld_32x32b_x32(lane_base + 384 + par * 64 + (2 * hl + b) * HD, o[hl]);
+          }
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.o_empty[par]);
+        if (row_ok) {
+          float* dst = agg + ((int64_t)ns.node * F + row) * kD;
 #pragma unroll
-          for (int x = 0; x < HD; x += 4)
-            o4[x >> 2] = make_float4(a[x * 256] * ns.inv_deg, a[(x + 1) * 256] * ns.inv_deg,
-                                     a[(x + 2) * 256] * ns.inv_deg, a[(x + 3) * 256] * ns.inv_deg);
+          for (int hl = 0; hl < HL; ++hl) {
+            float4* o4 = reinterpret_cast<float4*>(dst + (2 * hl + b) * HD);
+#pragma unroll
+            for (int x = 0; x < HD; x += 4)
+              o4[x >> 2] = make_float4(__uint_as_float(o[hl][x]) * ns.inv_deg, __uint_as_float(o[hl][x + 1]) * ns.inv_deg,
+                                       __uint_as_float(o[hl][x + 2]) * ns.inv_deg, __uint_as_float(o[hl][x + 3]) * ns.inv_deg);
+          }
         }
       }
       AMP_PHASE(9);

@@ -27,7 +27,7 @@ using namespace umma;
 
 constexpr int kD = 64;
 constexpr int kTileBytes = 128 * 128;
-constexpr int kThreads = 320;
+constexpr int kThreads = 384;   // 2 elementwise warpgroups + producer warp + 3 MMA-issuing warps
 constexpr int MODE_DQ = 0, MODE_DKV = 1;
 constexpr int kStatFloats = 4 * 128;   // H * roundup4(F) <= 512 floats per edge and statistic
 
@@ -90,7 +90,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sm.own_full[i], 1);
-      mbar_init(&sm.own_empty[i], 1 + 8);
+      mbar_init(&sm.own_empty[i], 1 + 8 + 2);
       mbar_init(&sm.xy_full[i], 1);
       mbar_init(&sm.xy_empty[i], 4);
       mbar_init(&sm.u_full[i], 4);
@@ -98,7 +98,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
     }
     for (int i = 0; i < NS; ++i) {
       mbar_init(&sm.edge_full[i], 1);
-      mbar_init(&sm.edge_empty[i], MODE == MODE_DKV ? 1 + 8 : 1);
+      mbar_init(&sm.edge_empty[i], MODE == MODE_DKV ? 3 + 8 : 3);
     }
     fence_barrier_init();
   }
@@ -189,83 +189,75 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       if (node < 0) break;
     }
   } else if (warp == 9) {
-    // ------------------------------------------------------------------ MMA issuer
-    // Two cursors over the global item sequence (item = edge * H + head): X/Y score MMAs and the T MMAs that
-    // consume the bf16 operands a warpgroup wrote back.  Waits of the first cursor keep servicing the second.
+    // ------------------------------------------------------------------ score MMAs X, Y (all heads)
     {
       const uint32_t idesc_xy = idesc_bf16(128, nqk, 0, 0);
-      const uint32_t idesc_t = idesc_bf16(128, HD, 0, 1);
-      uint32_t qi = 0, g_xy = 0, g_t = 0;
-      // T MMAs: TX = X' * B_tx, TY = Y' * B_ty (B operands MN-major from the edge tiles)
-      auto service_t = [&]() -> bool {
-        if (g_t >= g_xy) return false;
-        const uint32_t h = g_t % H, edge = g_t / H, b = h & 1;
-        const uint32_t cc = edge * HL + (h >> 1), st = edge % NS;
-        if (!mbar_test_wait(&sm.u_full[b], cc & 1)) return false;
-        tc_fence_after();
-        const uint32_t x_col = tmem + b * 256, y_col = x_col + 128;
-        const uint32_t btx = smem_u32(sm.edge[st][MODE == MODE_DQ ? 0 : 1]) + h * (HD * 2);
-        const uint32_t bty = smem_u32(sm.edge[st][0]) + h * (HD * 2);
-        for (int ks = 0; ks < ksteps; ++ks)
-          mma_ts_w(x_col + 64, x_col + 8 * ks, smem_desc(btx + ks * 2048, 16, 1024, LAYOUT_SW128), idesc_t, ks > 0);
-        for (int ks = 0; ks < ksteps; ++ks)
-          mma_ts_w(y_col + 64, y_col + 8 * ks, smem_desc(bty + ks * 2048, 16, 1024, LAYOUT_SW128), idesc_t, ks > 0);
-        mma_commit_w(&sm.t_full[b]);
-        if (h == H - 1) mma_commit_w(&sm.edge_empty[st]);
-        ++g_t;
-        return true;
-      };
-      auto wait_serving = [&](uint64_t* bar, uint32_t parity) -> bool {
-        uint64_t t0 = 0;
-        for (uint32_t spins = 0;; ++spins) {
-          if (mbar_test_wait(bar, parity)) return true;
-          if (service_t()) { t0 = 0; continue; }
-          __nanosleep(20);
-          if ((spins & 255) == 255) {
-            const uint64_t now = global_timer_ns();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 250000000ull) return false;
-          }
-        }
-      };
-      for (;;) {
+      uint32_t qi = 0, edge = 0;
+      for (;; ++qi) {
         const uint32_t qb = qi & 1;
-        if (!wait_serving(&sm.own_full[qb], (qi >> 1) & 1)) AMP_FAIL(201);
+        AMP_WAIT(&sm.own_full[qb], (qi >> 1) & 1, 201);
         const NodeSlot ns = sm.slot[qb];
         if (ns.node < 0) break;
-        for (int e = ns.e_begin; e < ns.e_end; ++e) {
-          const uint32_t edge = g_xy / H, st = edge % NS;
-          if (!wait_serving(&sm.edge_full[st], (edge / NS) & 1)) AMP_FAIL(202);
+        for (int e = ns.e_begin; e < ns.e_end; ++e, ++edge) {
+          const uint32_t st = edge % NS;
+          AMP_WAIT(&sm.edge_full[st], (edge / NS) & 1, 202);
 #pragma unroll
           for (int h = 0; h < H; ++h) {
             const uint32_t b = h & 1;
             const uint32_t cc = edge * HL + (h >> 1);
-            if (!wait_serving(&sm.xy_empty[b], (cc & 1) ^ 1)) AMP_FAIL(203);
+            AMP_WAIT(&sm.xy_empty[b], (cc & 1) ^ 1, 203);
             tc_fence_after();
             const uint32_t hb = h * (HD * 2);
-            const uint32_t a0 = smem_u32(sm.own[qb][0]) + hb, a1 = smem_u32(sm.own[qb][1]) + hb;
-            const uint32_t b0 = smem_u32(sm.edge[st][0]) + hb, b1 = smem_u32(sm.edge[st][1]) + hb;
+            const uint64_t a0 = smem_desc(smem_u32(sm.own[qb][0]) + hb, 16, 1024, LAYOUT_SW128);
+            const uint64_t a1 = smem_desc(smem_u32(sm.own[qb][1]) + hb, 16, 1024, LAYOUT_SW128);
+            const uint64_t b0 = smem_desc(smem_u32(sm.edge[st][0]) + hb, 16, 1024, LAYOUT_SW128);
+            const uint64_t b1 = smem_desc(smem_u32(sm.edge[st][1]) + hb, 16, 1024, LAYOUT_SW128);
 #pragma unroll
             for (int ks = 0; ks < HD / 16; ++ks)
-              mma_ss_w(tmem + b * 256, smem_desc(a0 + ks * 32, 16, 1024, LAYOUT_SW128),
-                     smem_desc(b0 + ks * 32, 16, 1024, LAYOUT_SW128), idesc_xy, ks > 0);
+              mma_ss_w(tmem + b * 256, desc_advance(a0, ks * 32), desc_advance(b0, ks * 32), idesc_xy, ks > 0);
 #pragma unroll
             for (int ks = 0; ks < HD / 16; ++ks)
-              mma_ss_w(tmem + b * 256 + 128, smem_desc(a1 + ks * 32, 16, 1024, LAYOUT_SW128),
-                     smem_desc(b1 + ks * 32, 16, 1024, LAYOUT_SW128), idesc_xy, ks > 0);
+              mma_ss_w(tmem + b * 256 + 128, desc_advance(a1, ks * 32), desc_advance(b1, ks * 32), idesc_xy, ks > 0);
             mma_commit_w(&sm.xy_full[b]);
-            if (e + 1 == ns.e_end && h == H - 1) mma_commit_w(&sm.own_empty[qb]);
-            ++g_xy;
-            service_t();
           }
+          mma_commit_w(&sm.edge_empty[st]);
+          if (e + 1 == ns.e_end) mma_commit_w(&sm.own_empty[qb]);
         }
-        ++qi;
       }
-      {
-        uint64_t t0 = global_timer_ns();
-        while (g_t < g_xy) {
-          if (service_t()) { t0 = global_timer_ns(); continue; }
-          if (global_timer_ns() - t0 > 250000000ull) AMP_FAIL(205);
+    }
+  } else if (warp >= 10) {
+    // ------------------------------------------------------------------ T MMAs for elementwise warpgroup b = warp - 10:
+    //   TX = X' * B_tx, TY = Y' * B_ty (A from TMEM, B operands MN-major from the edge tiles)
+    {
+      const uint32_t b = warp - 10;
+      const uint32_t idesc_t = idesc_bf16(128, HD, 0, 1);
+      uint32_t qi = 0, edge = 0, c = 0;
+      for (;; ++qi) {
+        const uint32_t qb = qi & 1;
+        AMP_WAIT(&sm.own_full[qb], (qi >> 1) & 1, 211);
+        const NodeSlot ns = sm.slot[qb];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.own_empty[qb]);
+        if (ns.node < 0) break;
+        for (int e = ns.e_begin; e < ns.e_end; ++e, ++edge) {
+          const uint32_t st = edge % NS;
+#pragma unroll
+          for (int hl = 0; hl < HL; ++hl, ++c) {
+            const int h = 2 * hl + b;
+            AMP_WAIT(&sm.u_full[b], c & 1, 213);
+            tc_fence_after();
+            const uint32_t x_col = tmem + b * 256, y_col = x_col + 128;
+            const uint64_t dtx = smem_desc(smem_u32(sm.edge[st][MODE == MODE_DQ ? 0 : 1]) + h * (HD * 2), 16, 1024, LAYOUT_SW128);
+            const uint64_t dty = smem_desc(smem_u32(sm.edge[st][0]) + h * (HD * 2), 16, 1024, LAYOUT_SW128);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              if (ks < ksteps) mma_ts_w(x_col + 64, x_col + 8 * ks, desc_advance(dtx, ks * 2048), idesc_t, ks > 0);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              if (ks < ksteps) mma_ts_w(y_col + 64, y_col + 8 * ks, desc_advance(dty, ks * 2048), idesc_t, ks > 0);
+            mma_commit_w(&sm.t_full[b]);
+          }
+          mma_commit_w(&sm.edge_empty[st]);
         }
       }
     }

@@ -182,17 +182,33 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 // lane executes the instruction.  Keeping the warp converged lets the compiler hold descriptors in uniform
 // registers; issuing from a divergent single-lane region costs a register-to-uniform broadcast loop per MMA.
 __device__ __forceinline__ void mma_ss_w(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  if (elect_one()) mma_ss(tmem_d, desc_a, desc_b, idesc, accumulate);
-  __syncwarp();
+  asm volatile(
+      "{\n\t.reg .pred pe, pa;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pa, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pa;\n\t}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 __device__ __forceinline__ void mma_ts_w(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  if (elect_one()) mma_ts(tmem_d, tmem_a, desc_b, idesc, accumulate);
-  __syncwarp();
+  asm volatile(
+      "{\n\t.reg .pred pe, pa;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pa, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, pa;\n\t}\n"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 __device__ __forceinline__ void mma_commit_w(uint64_t* bar) {
-  if (elect_one()) mma_commit(bar);
-  __syncwarp();
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n"
+      ::"r"(smem_u32(bar))
+      : "memory");
 }
+// descriptor with a byte offset added to its start address (offset must keep the address inside the 14-bit field)
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t byte_offset) { return desc + (byte_offset >> 4); }
 
 // ------------------------------------------------------------------------------------------
 // TMEM <-> registers.  32x32b shape: thread t of warp w touches lane 32*(w%4)+t, consecutive columns.
@@ -236,6 +252,11 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // first source -> upper half
+  return r;
+}
+__device__ __forceinline__ uint32_t mul_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
   return r;
 }
 __device__ __forceinline__ float ex2_approx(float x) {

@@ -25,7 +25,7 @@ def main():
                   _lib.i64(n), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(h), ws, _lib.size_t(256), st, prof)
     torch.cuda.synchronize()
     p = prof.cpu().tolist()
-    names = ["wait S", "load S", "max", "wait P slot", "exp+pack+st", "publish P + lse", "wait O", "accumulate O",
+    names = ["wait S", "load S", "max", "wait P slot", "exp+pack+scale", "st P + publish + lse", "wait O (node end)", "-",
              "node wait", "node epilogue"]
     items = max(1, p[10])
     tot = sum(p[:10])
@@ -33,7 +33,7 @@ def main():
     for nm, c in zip(names, p[:10]):
         print(f"  {nm:18s} {c / items:8.1f} cyc/item  {100.0 * c / tot:5.1f}%")
     mi = max(1, p[15])
-    print(f"MMA thread: items={mi} total/item={p[12] / mi:.0f} issue-QK/item={p[13] / mi:.0f} issue-PV/item={p[14] / mi:.0f} "
+    if p[15] > 0: print(f"MMA thread: items={mi} total/item={p[12] / mi:.0f} issue-QK/item={p[13] / mi:.0f} issue-PV/item={p[14] / mi:.0f} "
           f"idle/item={(p[12] - p[13] - p[14]) / mi:.0f}")
 
 if __name__ == "__main__":
