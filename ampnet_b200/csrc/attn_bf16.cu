@@ -384,7 +384,7 @@ extern "C" int ampconv_attn_bf16_supported(int F, int d, int H) {
 static int attn_fwd_bf16_impl(const void* q, const void* k, const void* v,
                               const int32_t* dst_rowptr, const int32_t* dst_src, const float* inv_deg,
                               const int32_t* order, float* agg, float* lse2,
-                              int64_t N, int64_t E, int F, int d, int H,
+                              int64_t N, int64_t N_kv, int64_t E, int F, int d, int H,
                               void* workspace, size_t workspace_bytes, void* stream_, long long* prof) {
   AMPCONV_REQUIRE(N >= 0 && E >= 0 && F > 0 && d > 0 && H > 0 && d % H == 0);
   if (!ampconv_attn_bf16_supported(F, d, H)) return AMPCONV_ERR_UNSUPPORTED;
@@ -393,8 +393,8 @@ static int attn_fwd_bf16_impl(const void* q, const void* k, const void* v,
   if (workspace_bytes < 256) return AMPCONV_ERR_WORKSPACE;
   cudaStream_t stream = as_stream(stream_);
   CUtensorMap mq, mk, mv;
-  if (!make_tensor_map_bf16_3d(&mq, q, kD, F, N, kD, 128) || !make_tensor_map_bf16_3d(&mk, k, kD, F, N, kD, 128) ||
-      !make_tensor_map_bf16_3d(&mv, v, kD, F, N, kD, 128))
+  if (!make_tensor_map_bf16_3d(&mq, q, kD, F, N, kD, 128) || !make_tensor_map_bf16_3d(&mk, k, kD, F, N_kv, kD, 128) ||
+      !make_tensor_map_bf16_3d(&mv, v, kD, F, N_kv, kD, 128))
     return AMPCONV_ERR_CUDA;
   int* counter = reinterpret_cast<int*>(workspace);
   int* status = counter + 1;
@@ -424,7 +424,7 @@ extern "C" int ampconv_attn_fwd_bf16(const void* q, const void* k, const void* v
                                      const int32_t* order, float* agg, float* lse2,
                                      int64_t N, int64_t E, int F, int d, int H,
                                      void* workspace, size_t workspace_bytes, void* stream_) {
-  return attn_fwd_bf16_impl(q, k, v, dst_rowptr, dst_src, inv_deg, order, agg, lse2, N, E, F, d, H, workspace,
+  return attn_fwd_bf16_impl(q, k, v, dst_rowptr, dst_src, inv_deg, order, agg, lse2, N, N, E, F, d, H, workspace,
                             workspace_bytes, stream_, nullptr);
 }
 
@@ -436,8 +436,19 @@ extern "C" int ampconv_attn_fwd_bf16_profile(const void* q, const void* k, const
                                              const int32_t* order, float* agg, float* lse2,
                                              int64_t N, int64_t E, int F, int d, int H,
                                              void* workspace, size_t workspace_bytes, void* stream_, long long* prof) {
-  return attn_fwd_bf16_impl(q, k, v, dst_rowptr, dst_src, inv_deg, order, agg, lse2, N, E, F, d, H, workspace,
+  return attn_fwd_bf16_impl(q, k, v, dst_rowptr, dst_src, inv_deg, order, agg, lse2, N, N, E, F, d, H, workspace,
                             workspace_bytes, stream_, prof);
+}
+
+// Destination-partitioned variant (multi-GPU): q covers the num_nodes local destinations, k / v the num_kv_nodes rows of
+// the all-gathered tensors; dst_src holds ids into k / v.
+extern "C" int ampconv_attn_fwd_bf16_part(const void* q, const void* k, const void* v,
+                                          const int32_t* dst_rowptr, const int32_t* dst_src, const float* inv_deg,
+                                          float* agg, float* lse2, int64_t num_nodes, int64_t num_kv_nodes, int64_t E,
+                                          int F, int d, int H, void* workspace, size_t workspace_bytes, void* stream_) {
+  AMPCONV_REQUIRE(num_kv_nodes > 0 || E == 0);
+  return attn_fwd_bf16_impl(q, k, v, dst_rowptr, dst_src, inv_deg, nullptr, agg, lse2, num_nodes,
+                            num_kv_nodes > 0 ? num_kv_nodes : 1, E, F, d, H, workspace, workspace_bytes, stream_, nullptr);
 }
 
 // Reads back the protocol status word written by the bf16 kernels (0 = ok).  Synchronises the stream.

@@ -12,8 +12,12 @@
 //       X = K_h Q_h^T, Y = V_h dO_h^T;  P^T = exp2(X - lse2_col), dS^T = P^T o (Y - delta_col);
 //       TX = P^T dO_h -> dV_h,  TY = dS^T Q'_h -> dK_h.
 //
-// TMEM: warpgroup b owns columns [256b, 256b+256): X at +0, Y at +128; the bf16 operands P / W (or
-// P^T / dS^T) overwrite columns +0..63 of X / Y in place; TX / TY land in columns +64.. of X / Y.
+// Work split: an item = (edge, head).  Its two score tiles X, Y live in one of two TMEM sets (item parity:
+// columns [256s, 256s+256), X at +0, Y at +128), so the score MMAs of item c+1 run while item c is being
+// processed.  All 8 elementwise warps work on the same item: warpgroup b owns score columns [64b, 64b+64)
+// of every row; the bf16 operands P / W (or P^T / dS^T) overwrite the fp32 scores in place (packed columns
+// +0..31 for score columns 0..63, +64..95 for 64..127); TX / TY land in columns +32.. of X / Y.
+// tcgen05 issue costs ~100 clk per instruction, so three converged warps issue: X/Y, TX and TY.
 #include <cuda_bf16.h>
 #include <math_constants.h>
 
@@ -46,6 +50,7 @@ struct BwdSmem {
   uint64_t own_full[2], own_empty[2];
   uint64_t edge_full[NS], edge_empty[NS];
   uint64_t xy_full[2], xy_empty[2], u_full[2], t_full[2];
+  float dl[2][2][128];                  // MODE_DQ: partial delta of [set][warpgroup][row]
   NodeSlot slot[2];
   uint32_t tmem_base;
 };
@@ -69,18 +74,18 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
 // own0/own1: tensor maps of the per-node tiles, oth0/oth1: of the per-edge tiles.
 // rowptr/nbr: CSR of the pass (by destination for MODE_DQ, by source for MODE_DKV); slot_of[e] = position of
 // edge e in the statistics arrays (NULL: identity).  d_qkv: fp32 [rows, 192].
-template <int HD, int MODE>
+template <int HD, int MODE, bool PROF>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_constant__ CUtensorMap own1,
                      const __grid_constant__ CUtensorMap oth0, const __grid_constant__ CUtensorMap oth1,
                      const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr,
                      const int32_t* __restrict__ slot_of, const float* __restrict__ lse2, float* __restrict__ delta,
                      float* __restrict__ d_qkv, int* __restrict__ counter, int* __restrict__ status,
-                     int N, int F, float out_scale0, float out_scale1) {
+                     int N, int F, float out_scale0, float out_scale1, int out_ld, int out_c0, int out_c1,
+                     long long* __restrict__ prof) {
   using Smem = BwdSmem<MODE>;
   constexpr int NS = Smem::NS;
-  constexpr int H = kD / HD, HL = H / 2;
-  static_assert(H % 2 == 0, "heads are split between two warpgroups");
+  constexpr int H = kD / HD;
   extern __shared__ uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -92,9 +97,9 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       mbar_init(&sm.own_full[i], 1);
       mbar_init(&sm.own_empty[i], 1 + 8 + 2);
       mbar_init(&sm.xy_full[i], 1);
-      mbar_init(&sm.xy_empty[i], 4);
-      mbar_init(&sm.u_full[i], 4);
-      mbar_init(&sm.t_full[i], 1);
+      mbar_init(&sm.xy_empty[i], 8);
+      mbar_init(&sm.u_full[i], 8);
+      mbar_init(&sm.t_full[i], 2);
     }
     for (int i = 0; i < NS; ++i) {
       mbar_init(&sm.edge_full[i], 1);
@@ -134,11 +139,11 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       ee = __shfl_sync(0xffffffffu, ee, 0);
       if (node >= 0 && ee == eb) {
         // node without edges in this pass: its gradient rows are zero
-        const int ncol = MODE == MODE_DQ ? kD : 2 * kD;
-        const int col0 = MODE == MODE_DQ ? 0 : kD;
-        for (int i = lane; i < F * (ncol / 4); i += 32) {
-          const int r = i / (ncol / 4), c4 = i - r * (ncol / 4);
-          *reinterpret_cast<float4*>(d_qkv + ((int64_t)node * F + r) * (3 * kD) + col0 + 4 * c4) =
+        const int nblk = MODE == MODE_DQ ? 1 : 2;
+        for (int i = lane; i < F * nblk * (kD / 4); i += 32) {
+          const int r = i / (nblk * (kD / 4)), rem = i - r * (nblk * (kD / 4));
+          const int blk = rem / (kD / 4), c4 = rem - blk * (kD / 4);
+          *reinterpret_cast<float4*>(d_qkv + ((int64_t)node * F + r) * out_ld + (blk == 0 ? out_c0 : out_c1) + 4 * c4) =
               make_float4(0.f, 0.f, 0.f, 0.f);
         }
         continue;
@@ -189,10 +194,10 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       if (node < 0) break;
     }
   } else if (warp == 9) {
-    // ------------------------------------------------------------------ score MMAs X, Y (all heads)
+    // ------------------------------------------------------------------ score MMAs X, Y of every item
     {
       const uint32_t idesc_xy = idesc_bf16(128, nqk, 0, 0);
-      uint32_t qi = 0, edge = 0;
+      uint32_t qi = 0, edge = 0, c = 0;
       for (;; ++qi) {
         const uint32_t qb = qi & 1;
         AMP_WAIT(&sm.own_full[qb], (qi >> 1) & 1, 201);
@@ -202,10 +207,9 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
           const uint32_t st = edge % NS;
           AMP_WAIT(&sm.edge_full[st], (edge / NS) & 1, 202);
 #pragma unroll
-          for (int h = 0; h < H; ++h) {
-            const uint32_t b = h & 1;
-            const uint32_t cc = edge * HL + (h >> 1);
-            AMP_WAIT(&sm.xy_empty[b], (cc & 1) ^ 1, 203);
+          for (int h = 0; h < H; ++h, ++c) {
+            const uint32_t set = c & 1;
+            AMP_WAIT(&sm.xy_empty[set], ((c >> 1) & 1) ^ 1, 203);
             tc_fence_after();
             const uint32_t hb = h * (HD * 2);
             const uint64_t a0 = smem_desc(smem_u32(sm.own[qb][0]) + hb, 16, 1024, LAYOUT_SW128);
@@ -214,11 +218,11 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
             const uint64_t b1 = smem_desc(smem_u32(sm.edge[st][1]) + hb, 16, 1024, LAYOUT_SW128);
 #pragma unroll
             for (int ks = 0; ks < HD / 16; ++ks)
-              mma_ss_w(tmem + b * 256, desc_advance(a0, ks * 32), desc_advance(b0, ks * 32), idesc_xy, ks > 0);
+              mma_ss_w(tmem + set * 256, desc_advance(a0, ks * 32), desc_advance(b0, ks * 32), idesc_xy, ks > 0);
 #pragma unroll
             for (int ks = 0; ks < HD / 16; ++ks)
-              mma_ss_w(tmem + b * 256 + 128, desc_advance(a1, ks * 32), desc_advance(b1, ks * 32), idesc_xy, ks > 0);
-            mma_commit_w(&sm.xy_full[b]);
+              mma_ss_w(tmem + set * 256 + 128, desc_advance(a1, ks * 32), desc_advance(b1, ks * 32), idesc_xy, ks > 0);
+            mma_commit_w(&sm.xy_full[set]);
           }
           mma_commit_w(&sm.edge_empty[st]);
           if (e + 1 == ns.e_end) mma_commit_w(&sm.own_empty[qb]);
@@ -226,11 +230,12 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       }
     }
   } else if (warp >= 10) {
-    // ------------------------------------------------------------------ T MMAs for elementwise warpgroup b = warp - 10:
-    //   TX = X' * B_tx, TY = Y' * B_ty (A from TMEM, B operands MN-major from the edge tiles)
+    // ------------------------------------------------------------------ T MMAs: warp 10 issues TX = X' * B_tx, warp 11 TY = Y' * B_ty
+    //   (A = the bf16 operand the elementwise warps wrote back into TMEM, B = an edge tile as MN-major operand)
     {
-      const uint32_t b = warp - 10;
+      const uint32_t which = warp - 10;                       // 0: TX, 1: TY
       const uint32_t idesc_t = idesc_bf16(128, HD, 0, 1);
+      const int btile = (which == 0 && MODE == MODE_DKV) ? 1 : 0;   // TX of the dK/dV pass multiplies dO; all others tile 0
       uint32_t qi = 0, edge = 0, c = 0;
       for (;; ++qi) {
         const uint32_t qb = qi & 1;
@@ -242,104 +247,111 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
         for (int e = ns.e_begin; e < ns.e_end; ++e, ++edge) {
           const uint32_t st = edge % NS;
 #pragma unroll
-          for (int hl = 0; hl < HL; ++hl, ++c) {
-            const int h = 2 * hl + b;
-            AMP_WAIT(&sm.u_full[b], c & 1, 213);
+          for (int h = 0; h < H; ++h, ++c) {
+            const uint32_t set = c & 1;
+            AMP_WAIT(&sm.u_full[set], (c >> 1) & 1, 213);
             tc_fence_after();
-            const uint32_t x_col = tmem + b * 256, y_col = x_col + 128;
-            const uint64_t dtx = smem_desc(smem_u32(sm.edge[st][MODE == MODE_DQ ? 0 : 1]) + h * (HD * 2), 16, 1024, LAYOUT_SW128);
-            const uint64_t dty = smem_desc(smem_u32(sm.edge[st][0]) + h * (HD * 2), 16, 1024, LAYOUT_SW128);
+            const uint32_t a_col = tmem + set * 256 + which * 128;
+            const uint64_t bd = smem_desc(smem_u32(sm.edge[st][btile]) + h * (HD * 2), 16, 1024, LAYOUT_SW128);
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)
-              if (ks < ksteps) mma_ts_w(x_col + 64, x_col + 8 * ks, desc_advance(dtx, ks * 2048), idesc_t, ks > 0);
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks)
-              if (ks < ksteps) mma_ts_w(y_col + 64, y_col + 8 * ks, desc_advance(dty, ks * 2048), idesc_t, ks > 0);
-            mma_commit_w(&sm.t_full[b]);
+              if (ks < ksteps)
+                mma_ts_w(a_col + 32, a_col + (ks < 4 ? 8 * ks : 64 + 8 * (ks - 4)), desc_advance(bd, ks * 2048), idesc_t, ks > 0);
+            mma_commit_w(&sm.t_full[set]);
           }
           mma_commit_w(&sm.edge_empty[st]);
         }
       }
     }
   } else {
-    // ------------------------------------------------------------------ elementwise warpgroups
+    // ------------------------------------------------------------------ elementwise warps: warpgroup b owns score columns [64b, 64b+64)
     const uint32_t b = warp >> 2;
     const int row = (warp & 3) * 32 + lane;
     const bool row_ok = row < F;
-    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + b * 256;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    constexpr int HH = HD / 2;                      // T columns this thread reads back per head
     uint32_t qi = 0, c = 0, ei = 0;
-    float* acc = &sm.acc[0][b * 128 + row];
+    float* acc = &sm.acc[0][b * 128 + row];         // element x of this thread: acc[x * 256]
+    const bool do_prof = PROF && blockIdx.x == 0;
+    long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tp = do_prof ? clock64() : 0;
+#define AMP_PHASE(i) do { if (do_prof) { const long long now_ = clock64(); pt[i] += now_ - tp; tp = now_; } } while (0)
     for (;;) {
       const uint32_t qb = qi & 1;
       AMP_WAIT(&sm.own_full[qb], (qi >> 1) & 1, 301);
+      AMP_PHASE(6);
       const NodeSlot ns = sm.slot[qb];
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.own_empty[qb]);
       if (ns.node < 0) break;
 #pragma unroll
-      for (int x = 0; x < Smem::NACC * HL * HD; ++x) acc[x * 256] = 0.f;
-      float dl_prev = 0.f;
+      for (int x = 0; x < Smem::NACC * H * HH; ++x) acc[x * 256] = 0.f;
       uint32_t t = 0;
-      // folds TX / TY of this warpgroup's item into the accumulators of local head hl_prev and frees X / Y
-      auto readback = [&](uint32_t cc, int hl_prev, float dl) -> bool {
-        if (!mbar_wait(&sm.t_full[b], cc & 1)) return false;
+      int e_prev = 0;
+      // folds this thread's half of TX / TY of item cc (head hp, edge slot ep) into the accumulators, frees the set
+      auto readback = [&](uint32_t cc, int hp, int ep) -> bool {
+        const uint32_t set = cc & 1;
+        if (!mbar_wait(&sm.t_full[set], (cc >> 1) & 1)) return false;
+        AMP_PHASE(3);
         tc_fence_after();
-        uint32_t tx[HD], ty[HD];
-        if constexpr (HD == 16) {
-          tmem_ld_32x32b_x16(lane_base + 64, tx);
-          tmem_ld_32x32b_x16(lane_base + 128 + 64, ty);
+        uint32_t tx[HH], ty[HH];
+        const uint32_t base = lane_base + set * 256 + 32 + HH * b;
+        if constexpr (HH == 8) {
+          tmem_ld_32x32b_x8(base, tx);
+          tmem_ld_32x32b_x8(base + 128, ty);
         } else {
-          tmem_ld_32x32b_x32(lane_base + 64, tx);
-          tmem_ld_32x32b_x32(lane_base + 128 + 64, ty);
+          tmem_ld_32x32b_x16(base, tx);
+          tmem_ld_32x32b_x16(base + 128, ty);
         }
         tmem_ld_wait();
+        const float dl = (MODE == MODE_DQ) ? sm.dl[set][0][row] + sm.dl[set][1][row] : 0.f;   // before the set is released
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.xy_empty[b]);
-        float* a = acc + hl_prev * HD * 256;
+        if (lane == 0) mbar_arrive(&sm.xy_empty[set]);
+        float* a = acc + hp * HH * 256;
         if (MODE == MODE_DQ) {
+          if (b == 0 && row_ok) delta[((int64_t)ep * H + hp) * Fs + row] = dl;
 #pragma unroll
-          for (int x = 0; x < HD; ++x)
-            a[x * 256] += __uint_as_float(ty[x]) - dl * __uint_as_float(tx[x]);
+          for (int x = 0; x < HH; ++x) a[x * 256] += __uint_as_float(ty[x]) - dl * __uint_as_float(tx[x]);
         } else {
-          float* a2 = a + HL * HD * 256;
+          float* a2 = a + H * HH * 256;
 #pragma unroll
-          for (int x = 0; x < HD; ++x) {
+          for (int x = 0; x < HH; ++x) {
             a[x * 256] += __uint_as_float(ty[x]);    // dK
             a2[x * 256] += __uint_as_float(tx[x]);   // dV
           }
         }
+        AMP_PHASE(4);
         return true;
       };
       for (int e = ns.e_begin; e < ns.e_end; ++e, ++ei) {
         const uint32_t st = ei % NS;
-        const int64_t sl = (MODE == MODE_DQ) ? (int64_t)e : 0;
         if (MODE == MODE_DKV) AMP_WAIT(&sm.edge_full[st], (ei / NS) & 1, 306);   // acquire the bulk-copied statistics rows
 #pragma unroll
-        for (int hl = 0; hl < HL; ++hl) {
-          const int h = 2 * hl + b;
-          // the previous item of this warpgroup must leave X / Y before the MMA warp can refill them
-          if (t > 0) {
-            if (!readback(c - 1, (hl + HL - 1) % HL, dl_prev)) AMP_FAIL(304);
-          }
+        for (int h = 0; h < H; ++h) {
+          const uint32_t set = c & 1;
           float L = 0.f;
-          if (MODE == MODE_DQ) L = row_ok ? lse2[(sl * H + h) * Fs + row] : 0.f;
-          AMP_WAIT(&sm.xy_full[b], c & 1, 302);
+          if (MODE == MODE_DQ) L = row_ok ? lse2[((int64_t)e * H + h) * Fs + row] : 0.f;
+          AMP_PHASE(5);
+          AMP_WAIT(&sm.xy_full[set], (c >> 1) & 1, 302);
+          AMP_PHASE(0);
           tc_fence_after();
           const float* Ls = sm.stat[st][0] + h * Fs;
           const float* Ds = sm.stat[st][1] + h * Fs;
+          const uint32_t xbase = lane_base + set * 256;
           float dl0 = 0.f, dl1 = 0.f;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (32 * k < nqk) {
+          for (int k = 0; k < 2; ++k) {
+            const int col0 = 64 * b + 32 * k;          // first score column of this chunk
+            if (col0 < nqk) {
               uint32_t xs[32], ys[32];
-              tmem_ld_32x32b_x32(lane_base + 32 * k, xs);
-              tmem_ld_32x32b_x32(lane_base + 128 + 32 * k, ys);
+              tmem_ld_32x32b_x32(xbase + col0, xs);
+              tmem_ld_32x32b_x32(xbase + 128 + col0, ys);
               tmem_ld_wait();
               uint32_t px[16], py[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                const int c0 = 32 * k + 2 * j;
+                const int c0 = col0 + 2 * j;
                 float p0, p1, u0, u1;
                 if (MODE == MODE_DQ) {
                   p0 = ex2_approx(__uint_as_float(xs[2 * j]) - L);
@@ -363,51 +375,61 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
                 px[j] = pack_bf16x2(p0, p1);
                 py[j] = pack_bf16x2(u0, u1);
               }
-              tmem_st_32x32b_x16(lane_base + 16 * k, px);
-              tmem_st_32x32b_x16(lane_base + 128 + 16 * k, py);
+              // packed columns: score columns 0..63 -> +0..31, 64..127 -> +64..95 (always behind this thread's own reads)
+              tmem_st_32x32b_x16(xbase + 64 * b + 16 * k, px);
+              tmem_st_32x32b_x16(xbase + 128 + 64 * b + 16 * k, py);
             }
           }
+          if (MODE == MODE_DQ) sm.dl[set][b][row] = dl0 + dl1;
+          AMP_PHASE(1);
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&sm.u_full[b]);
-          const float dl = dl0 + dl1;
-          if (MODE == MODE_DQ) {
-            if (row_ok) delta[(sl * H + h) * Fs + row] = dl;
-          } else if (hl == HL - 1) {
-            __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.u_full[set]);
+          if (MODE == MODE_DKV && h == H - 1) {
             if (lane == 0) mbar_arrive(&sm.edge_empty[st]);   // this warp no longer reads the stage's statistics rows
           }
-          dl_prev = dl;
+          AMP_PHASE(2);
+          // the previous item's T tiles are complete by now: fold them in and release its set for the score MMAs
+          if (t > 0) {
+            if (!readback(c - 1, (h + H - 1) % H, e_prev)) AMP_FAIL(304);
+          }
+          e_prev = e;
           ++c;
           ++t;
         }
       }
       if (t > 0) {
-        if (!readback(c - 1, HL - 1, dl_prev)) AMP_FAIL(305);
+        if (!readback(c - 1, H - 1, e_prev)) AMP_FAIL(305);
       }
       if (row_ok) {
-        float* o = d_qkv + ((int64_t)ns.node * F + row) * (3 * kD);
+        float* o = d_qkv + ((int64_t)ns.node * F + row) * out_ld;
 #pragma unroll
-        for (int hl = 0; hl < HL; ++hl) {
-          const float* a = acc + hl * HD * 256;
-          float4* o0 = reinterpret_cast<float4*>(o + (MODE == MODE_DQ ? 0 : kD) + (2 * hl + b) * HD);
+        for (int h = 0; h < H; ++h) {
+          const float* a = acc + h * HH * 256;
+          float4* o0 = reinterpret_cast<float4*>(o + out_c0 + h * HD + HH * b);
 #pragma unroll
-          for (int x = 0; x < HD; x += 4)
+          for (int x = 0; x < HH; x += 4)
             o0[x >> 2] = make_float4(a[x * 256] * out_scale0, a[(x + 1) * 256] * out_scale0,
                                      a[(x + 2) * 256] * out_scale0, a[(x + 3) * 256] * out_scale0);
           if (MODE == MODE_DKV) {
-            const float* a2 = a + HL * HD * 256;
-            float4* o1 = reinterpret_cast<float4*>(o + 2 * kD + (2 * hl + b) * HD);
+            const float* a2 = a + H * HH * 256;
+            float4* o1 = reinterpret_cast<float4*>(o + out_c1 + h * HD + HH * b);
 #pragma unroll
-            for (int x = 0; x < HD; x += 4)
+            for (int x = 0; x < HH; x += 4)
               o1[x >> 2] = make_float4(a2[x * 256] * out_scale1, a2[(x + 1) * 256] * out_scale1,
                                        a2[(x + 2) * 256] * out_scale1, a2[(x + 3) * 256] * out_scale1);
           }
         }
       }
+      AMP_PHASE(7);
       ++qi;
     }
+    if (do_prof && threadIdx.x == 0) {
+      for (int i = 0; i < 8; ++i) prof[i] = pt[i];
+      prof[8] = c;
+    }
+#undef AMP_PHASE
   }
 fail:
   tc_fence_before();
@@ -415,15 +437,25 @@ fail:
   if (warp == 9) tmem_dealloc(tmem, 512);
 }
 
+long long* g_bwd_prof = nullptr;   // debug: set through ampconv_debug_set_bwd_profile
+
 template <int HD, int MODE>
 int launch_bwd(const CUtensorMap& own0, const CUtensorMap& own1, const CUtensorMap& oth0, const CUtensorMap& oth1,
                const int32_t* rowptr, const int32_t* nbr, const int32_t* slot_of, const float* lse2, float* delta,
-               float* d_qkv, int* counter, int* status, int N, int F, float s0, float s1, cudaStream_t stream) {
+               float* d_qkv, int* counter, int* status, int N, int F, float s0, float s1, int out_ld, int out_c0,
+               int out_c1, cudaStream_t stream) {
   const size_t smem = sizeof(BwdSmem<MODE>) + 1024;
-  AMPCONV_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_bf16_kernel<HD, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = N < sm_count() ? N : sm_count();
-  attn_bwd_bf16_kernel<HD, MODE><<<grid, kThreads, smem, stream>>>(own0, own1, oth0, oth1, rowptr, nbr, slot_of, lse2, delta,
-                                                                  d_qkv, counter, status, N, F, s0, s1);
+  long long* prof = g_bwd_prof;
+  if (prof) {
+    AMPCONV_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_bf16_kernel<HD, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_bwd_bf16_kernel<HD, MODE, true><<<grid, kThreads, smem, stream>>>(own0, own1, oth0, oth1, rowptr, nbr, slot_of, lse2, delta,
+                                                                          d_qkv, counter, status, N, F, s0, s1, out_ld, out_c0, out_c1, prof);
+  } else {
+    AMPCONV_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_bf16_kernel<HD, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_bwd_bf16_kernel<HD, MODE, false><<<grid, kThreads, smem, stream>>>(own0, own1, oth0, oth1, rowptr, nbr, slot_of, lse2, delta,
+                                                                           d_qkv, counter, status, N, F, s0, s1, out_ld, out_c0, out_c1, nullptr);
+  }
   AMPCONV_CHECK_LAUNCH();
   return AMPCONV_OK;
 }
@@ -435,20 +467,23 @@ using namespace ampconv;
 
 extern "C" int ampconv_attn_bf16_supported(int F, int d, int H);
 
+// N_own: nodes the pass iterates over (destinations for MODE_DQ, sources for MODE_DKV); N_oth: nodes of the edge tiles.
 static int bwd_common(int mode, const void* q, const void* k, const void* v, const void* d_agg_bf16,
                       const int32_t* rowptr, const int32_t* nbr, const int32_t* slot_of, const float* lse2, float* delta,
-                      float* d_qkv, int64_t N, int64_t E, int F, int d, int H, void* workspace, size_t workspace_bytes,
-                      void* stream_) {
-  AMPCONV_REQUIRE(N >= 0 && E >= 0 && F > 0 && d > 0 && H > 0 && d % H == 0);
+                      float* out, int out_ld, int out_c0, int out_c1, int64_t N_dst, int64_t N_kv, int64_t E, int F, int d,
+                      int H, void* workspace, size_t workspace_bytes, void* stream_) {
+  AMPCONV_REQUIRE(N_dst >= 0 && N_kv >= 0 && E >= 0 && F > 0 && d > 0 && H > 0 && d % H == 0);
   if (!ampconv_attn_bf16_supported(F, d, H)) return AMPCONV_ERR_UNSUPPORTED;
-  if (N == 0) return AMPCONV_OK;
-  AMPCONV_REQUIRE(q && k && v && d_agg_bf16 && rowptr && d_qkv && workspace);
+  const int64_t N_own = mode == MODE_DQ ? N_dst : N_kv;
+  if (N_own == 0) return AMPCONV_OK;
+  AMPCONV_REQUIRE(q && k && v && d_agg_bf16 && rowptr && out && workspace);
   AMPCONV_REQUIRE(E == 0 || (nbr && lse2 && delta));
   if (workspace_bytes < 256) return AMPCONV_ERR_WORKSPACE;
   cudaStream_t stream = as_stream(stream_);
   CUtensorMap mq, mk, mv, mg;
-  if (!make_tensor_map_bf16_3d(&mq, q, kD, F, N, kD, 128) || !make_tensor_map_bf16_3d(&mk, k, kD, F, N, kD, 128) ||
-      !make_tensor_map_bf16_3d(&mv, v, kD, F, N, kD, 128) || !make_tensor_map_bf16_3d(&mg, d_agg_bf16, kD, F, N, kD, 128))
+  const int64_t nd = N_dst > 0 ? N_dst : 1, nk = N_kv > 0 ? N_kv : 1;
+  if (!make_tensor_map_bf16_3d(&mq, q, kD, F, nd, kD, 128) || !make_tensor_map_bf16_3d(&mk, k, kD, F, nk, kD, 128) ||
+      !make_tensor_map_bf16_3d(&mv, v, kD, F, nk, kD, 128) || !make_tensor_map_bf16_3d(&mg, d_agg_bf16, kD, F, nd, kD, 128))
     return AMPCONV_ERR_CUDA;
   int* counter = reinterpret_cast<int*>(workspace) + (mode == MODE_DQ ? 2 : 4);
   int* status = reinterpret_cast<int*>(workspace) + 1;
@@ -459,25 +494,25 @@ static int bwd_common(int mode, const void* q, const void* k, const void* v, con
   if (mode == MODE_DQ) {
     // dQ = hd^-1/2 * (dS K)
     if (hd == 16)
-      return launch_bwd<16, MODE_DQ>(mq, mg, mk, mv, rowptr, nbr, slot_of, lse2, delta, d_qkv, counter, status, (int)N, F,
-                                    inv_sqrt_hd, 0.f, stream);
-    return launch_bwd<32, MODE_DQ>(mq, mg, mk, mv, rowptr, nbr, slot_of, lse2, delta, d_qkv, counter, status, (int)N, F,
-                                  inv_sqrt_hd, 0.f, stream);
+      return launch_bwd<16, MODE_DQ>(mq, mg, mk, mv, rowptr, nbr, slot_of, lse2, delta, out, counter, status, (int)N_own, F,
+                                    inv_sqrt_hd, 0.f, out_ld, out_c0, out_c1, stream);
+    return launch_bwd<32, MODE_DQ>(mq, mg, mk, mv, rowptr, nbr, slot_of, lse2, delta, out, counter, status, (int)N_own, F,
+                                  inv_sqrt_hd, 0.f, out_ld, out_c0, out_c1, stream);
   }
   // dK = hd^-1/2 * dS^T Q = ln2 * dS^T Q'  (Q' = Q * log2e / sqrt(hd)),  dV = P^T dO
   if (hd == 16)
-    return launch_bwd<16, MODE_DKV>(mk, mv, mq, mg, rowptr, nbr, slot_of, lse2, delta, d_qkv, counter, status, (int)N, F, ln2,
-                                   1.f, stream);
-  return launch_bwd<32, MODE_DKV>(mk, mv, mq, mg, rowptr, nbr, slot_of, lse2, delta, d_qkv, counter, status, (int)N, F, ln2,
-                                 1.f, stream);
+    return launch_bwd<16, MODE_DKV>(mk, mv, mq, mg, rowptr, nbr, slot_of, lse2, delta, out, counter, status, (int)N_own, F,
+                                   ln2, 1.f, out_ld, out_c0, out_c1, stream);
+  return launch_bwd<32, MODE_DKV>(mk, mv, mq, mg, rowptr, nbr, slot_of, lse2, delta, out, counter, status, (int)N_own, F, ln2,
+                                 1.f, out_ld, out_c0, out_c1, stream);
 }
 
 extern "C" int ampconv_attn_bwd_dq_bf16(const void* q, const void* k, const void* v, const void* d_agg_bf16,
                                         const float* lse2, const int32_t* dst_rowptr, const int32_t* dst_src,
                                         float* d_qkv, float* delta, int64_t N, int64_t E, int F, int d, int H,
                                         void* workspace, size_t workspace_bytes, void* stream) {
-  return bwd_common(MODE_DQ, q, k, v, d_agg_bf16, dst_rowptr, dst_src, nullptr, lse2, delta, d_qkv, N, E, F, d, H,
-                    workspace, workspace_bytes, stream);
+  return bwd_common(MODE_DQ, q, k, v, d_agg_bf16, dst_rowptr, dst_src, nullptr, lse2, delta, d_qkv, 3 * kD, 0, 0, N, N, E, F,
+                    d, H, workspace, workspace_bytes, stream);
 }
 
 extern "C" int ampconv_attn_bwd_dkv_bf16(const void* q, const void* k, const void* v, const void* d_agg_bf16,
@@ -486,5 +521,33 @@ extern "C" int ampconv_attn_bwd_dkv_bf16(const void* q, const void* k, const voi
                                          int64_t N, int64_t E, int F, int d, int H,
                                          void* workspace, size_t workspace_bytes, void* stream) {
   return bwd_common(MODE_DKV, q, k, v, d_agg_bf16, src_rowptr, src_dst, src_pos, lse2, const_cast<float*>(delta), d_qkv,
-                    N, E, F, d, H, workspace, workspace_bytes, stream);
+                    3 * kD, kD, 2 * kD, N, N, E, F, d, H, workspace, workspace_bytes, stream);
+}
+
+// Destination-partitioned variants (multi-GPU): q / d_agg cover the num_nodes local destinations, k / v the
+// num_kv_nodes rows of the all-gathered tensors.  _dq writes d_q fp32 [num_nodes*F, 64]; _dkv writes the partial
+// d_k | d_v fp32 [num_kv_nodes*F, 128] of the local edges (to be reduce-scattered to the owners).
+extern "C" int ampconv_attn_bwd_dq_bf16_part(const void* q, const void* k, const void* v, const void* d_agg_bf16,
+                                             const float* lse2, const int32_t* dst_rowptr, const int32_t* dst_src,
+                                             float* d_q, float* delta, int64_t num_nodes, int64_t num_kv_nodes, int64_t E,
+                                             int F, int d, int H, void* workspace, size_t workspace_bytes, void* stream) {
+  return bwd_common(MODE_DQ, q, k, v, d_agg_bf16, dst_rowptr, dst_src, nullptr, lse2, delta, d_q, kD, 0, 0, num_nodes,
+                    num_kv_nodes, E, F, d, H, workspace, workspace_bytes, stream);
+}
+
+extern "C" int ampconv_attn_bwd_dkv_bf16_part(const void* q, const void* k, const void* v, const void* d_agg_bf16,
+                                              const float* lse2, const float* delta, const int32_t* src_rowptr,
+                                              const int32_t* src_dst, const int32_t* src_pos, float* d_kv,
+                                              int64_t num_nodes, int64_t num_kv_nodes, int64_t E, int F, int d, int H,
+                                              void* workspace, size_t workspace_bytes, void* stream) {
+  return bwd_common(MODE_DKV, q, k, v, d_agg_bf16, src_rowptr, src_dst, src_pos, lse2, const_cast<float*>(delta), d_kv,
+                    2 * kD, 0, kD, num_nodes, num_kv_nodes, E, F, d, H, workspace, workspace_bytes, stream);
+}
+
+// Debug: when set to a device buffer of 9 int64, the next backward launches run the instrumented kernel and fill it
+// with the cycles one elementwise warp spent per phase (wait X/Y, chunks, publish, wait T, fold T, stats load,
+// node wait, node epilogue) and its item count.  NULL restores the product kernels.
+extern "C" int ampconv_debug_set_bwd_profile(long long* prof) {
+  ampconv::g_bwd_prof = prof;
+  return AMPCONV_OK;
 }

@@ -23,13 +23,13 @@ int sm_count() {
 
 namespace {
 
-__global__ void split_edges_kernel(const int64_t* __restrict__ edge_index, int64_t E, int64_t N,
+__global__ void split_edges_kernel(const int64_t* __restrict__ edge_index, int64_t E, int64_t N_src, int64_t N_dst,
                                    int32_t* __restrict__ src, int32_t* __restrict__ dst,
                                    int32_t* __restrict__ iota, int* __restrict__ bad) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= E) return;
   int64_t s = edge_index[i], t = edge_index[E + i];
-  if (s < 0 || s >= N || t < 0 || t >= N) {
+  if (s < 0 || s >= N_src || t < 0 || t >= N_dst) {
     atomicExch(bad, 1);
     s = 0;
     t = 0;
@@ -138,12 +138,12 @@ extern "C" int ampconv_graph_workspace_bytes(int64_t E, int64_t N, size_t* bytes
   return AMPCONV_OK;
 }
 
-extern "C" int ampconv_graph_build(const int64_t* edge_index, int64_t E, int64_t N,
+extern "C" int ampconv_graph_build_bipartite(const int64_t* edge_index, int64_t E, int64_t N, int64_t N_src,
                                    int32_t* dst_rowptr, int32_t* dst_src, int32_t* dst_eid,
                                    int32_t* src_rowptr, int32_t* src_dst, int32_t* src_pos,
                                    float* inv_deg, float* has_in,
                                    void* workspace, size_t workspace_bytes, void* stream_) {
-  AMPCONV_REQUIRE(E >= 0 && N >= 0 && E < (int64_t)INT32_MAX && N < (int64_t)INT32_MAX);
+  AMPCONV_REQUIRE(E >= 0 && N >= 0 && N_src >= 0 && E < (int64_t)INT32_MAX && N < (int64_t)INT32_MAX && N_src < (int64_t)INT32_MAX);
   AMPCONV_REQUIRE(dst_rowptr && src_rowptr && inv_deg && has_in && workspace);
   AMPCONV_REQUIRE(E == 0 || (edge_index && dst_src && dst_eid && src_dst && src_pos));
   cudaStream_t stream = as_stream(stream_);
@@ -154,10 +154,11 @@ extern "C" int ampconv_graph_build(const int64_t* edge_index, int64_t E, int64_t
   const int T = 256;
   AMPCONV_CUDA_TRY(cudaMemsetAsync(ws.bad, 0, sizeof(int), stream));
   int end_bit = 1;
-  while ((1ll << end_bit) < (N > 1 ? N : 2)) ++end_bit;   // keys are < N: sort only the bits in use
+  const int64_t n_max = N > N_src ? N : N_src;
+  while ((1ll << end_bit) < (n_max > 1 ? n_max : 2)) ++end_bit;   // keys are < max(N, N_src): sort only the bits in use
   if (E > 0) {
     unsigned gb = (unsigned)ceil_div<int64_t>(E, T);
-    split_edges_kernel<<<gb, T, 0, stream>>>(edge_index, E, N, ws.src, ws.dst, ws.iota, ws.bad);
+    split_edges_kernel<<<gb, T, 0, stream>>>(edge_index, E, N_src, N, ws.src, ws.dst, ws.iota, ws.bad);
     AMPCONV_CHECK_LAUNCH();
     // destination-sorted view (stable: ties keep edge_index order)
     size_t cub_bytes = ws.cub_bytes;
@@ -184,10 +185,19 @@ extern "C" int ampconv_graph_build(const int64_t* edge_index, int64_t E, int64_t
     gather_i32_kernel<<<gb, T, 0, stream>>>(ws.dst, src_pos, E, src_dst);
     AMPCONV_CHECK_LAUNCH();
   }
-  rowptr_kernel<<<gn, T, 0, stream>>>(ws.keys_out, E, N, src_rowptr);
+  rowptr_kernel<<<(unsigned)ceil_div<int64_t>(N_src + 1, T), T, 0, stream>>>(ws.keys_out, E, N_src, src_rowptr);
   AMPCONV_CHECK_LAUNCH();
   int bad_host = 0;
   AMPCONV_CUDA_TRY(cudaMemcpyAsync(&bad_host, ws.bad, sizeof(int), cudaMemcpyDeviceToHost, stream));
   AMPCONV_CUDA_TRY(cudaStreamSynchronize(stream));
   return bad_host ? AMPCONV_ERR_INDEX_RANGE : AMPCONV_OK;
+}
+
+extern "C" int ampconv_graph_build(const int64_t* edge_index, int64_t E, int64_t N,
+                                   int32_t* dst_rowptr, int32_t* dst_src, int32_t* dst_eid,
+                                   int32_t* src_rowptr, int32_t* src_dst, int32_t* src_pos,
+                                   float* inv_deg, float* has_in,
+                                   void* workspace, size_t workspace_bytes, void* stream_) {
+  return ampconv_graph_build_bipartite(edge_index, E, N, N, dst_rowptr, dst_src, dst_eid, src_rowptr, src_dst, src_pos,
+                                       inv_deg, has_in, workspace, workspace_bytes, stream_);
 }

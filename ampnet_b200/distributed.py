@@ -1,0 +1,213 @@
+"""Destination-partitioned AMPConv over one process per GPU.
+
+The reference has no working multi-GPU path (its gloo demo never synchronises,
+``experiments/cora_benchmark_graphsaint_distributed.py:63,83``).  Every edge is an independent attention
+problem and the aggregation is a sum per destination, so the path shards by destination:
+
+* destinations are range-partitioned into ``world`` contiguous ranges balanced by in-edge count;
+  rank r owns the rows of x / Q / out / dX of its range and projects K, V for its own nodes;
+* exchange step, forward: all-gather of the projected K and V (bf16) -- every rank then holds the
+  ``world * max_n`` padded rows its in-edges may reference (source ids are remapped to padded ids once);
+* exchange step, backward: each rank computes the partial dK | dV its local edges contribute to every source
+  and the partials are reduce-scattered to the owners; dQ never leaves the rank;
+* the four parameter gradients are all-reduced.
+
+Host logic only: the kernels are the ``*_part`` entry points of include/ampconv.h.  The collectives go through
+``torch.distributed`` (NCCL over NVLink on the GPU box; the CPU tests run the same host logic over gloo).
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from . import functional as F_
+
+
+# ------------------------------------------------------------------------------------------ partitioning (pure torch, CPU or GPU)
+def partition_ranges(in_degree, world):
+    """Boundaries [world + 1] of contiguous destination ranges with (nearly) equal in-edge counts."""
+    n = in_degree.numel()
+    csum = torch.cumsum(in_degree.to(torch.int64), 0)
+    total = int(csum[-1]) if n > 0 else 0
+    bounds = [0]
+    for r in range(1, world):
+        target = total * r // world
+        # first node index whose prefix sum exceeds the target (ties keep ranges non-empty where possible)
+        idx = int(torch.searchsorted(csum, torch.tensor(target, dtype=torch.int64, device=csum.device), right=True))
+        idx = max(idx, bounds[-1])
+        bounds.append(min(idx, n))
+    bounds.append(n)
+    return torch.tensor(bounds, dtype=torch.int64)
+
+
+def padded_id(node, bounds, max_n):
+    """Row of a global node id inside the all-gathered [world * max_n, ...] tensors."""
+    owner = torch.searchsorted(bounds.to(node.device), node, right=True) - 1
+    return owner * max_n + (node - bounds.to(node.device)[owner])
+
+
+class PartitionedGraph:
+    """Local view of rank ``rank``: edges whose destination it owns, destinations as local ids, sources as padded ids."""
+
+    def __init__(self, edge_index, num_nodes, world, rank, bounds=None):
+        src, dst = edge_index[0], edge_index[1]
+        if bounds is None:
+            bounds = partition_ranges(torch.bincount(dst, minlength=num_nodes).cpu(), world)
+        self.bounds = bounds
+        self.world, self.rank, self.num_nodes = world, rank, int(num_nodes)
+        self.lo, self.hi = int(bounds[rank]), int(bounds[rank + 1])
+        self.n_local = self.hi - self.lo
+        self.max_n = int((bounds[1:] - bounds[:-1]).max())
+        mine = (dst >= self.lo) & (dst < self.hi)
+        self.edge_ids = torch.nonzero(mine, as_tuple=False).squeeze(1)       # columns of the global edge_index
+        self.local_edge_index = torch.stack([padded_id(src[mine], bounds, self.max_n), dst[mine] - self.lo]).contiguous()
+        self.num_kv_nodes = world * self.max_n
+        self.graph = None                                                   # device CSR, built lazily
+
+    def device_graph(self):
+        if self.graph is None:
+            self.graph = BipartiteGraph(self.local_edge_index, self.n_local, self.num_kv_nodes)
+        return self.graph
+
+
+class BipartiteGraph:
+    """CSR by local destination and by padded source (ampconv_graph_build_bipartite)."""
+
+    def __init__(self, edge_index, num_dst, num_src):
+        if not edge_index.is_cuda:
+            raise TypeError("edge_index must be a CUDA tensor")
+        dev = edge_index.device
+        e = edge_index.size(1)
+        self.num_edges, self.num_nodes, self.num_src = e, int(num_dst), int(num_src)
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.dst_rowptr = torch.empty(num_dst + 1, **i32)
+        self.dst_src = torch.empty(e, **i32)
+        self.dst_eid = torch.empty(e, **i32)
+        self.src_rowptr = torch.empty(num_src + 1, **i32)
+        self.src_dst = torch.empty(e, **i32)
+        self.src_pos = torch.empty(e, **i32)
+        self.inv_deg = torch.empty(num_dst, dtype=torch.float32, device=dev)
+        self.has_in = torch.empty(num_dst, dtype=torch.float32, device=dev)
+        nbytes = ctypes.c_size_t(0)
+        with torch.cuda.device(dev):
+            _lib.call("ampconv_graph_workspace_bytes", _lib.i64(e), _lib.i64(max(num_dst, num_src)), ctypes.byref(nbytes))
+            ws = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=dev)
+            _lib.call("ampconv_graph_build_bipartite", edge_index.contiguous(), _lib.i64(e), _lib.i64(num_dst),
+                      _lib.i64(num_src), self.dst_rowptr, self.dst_src, self.dst_eid, self.src_rowptr, self.src_dst,
+                      self.src_pos, self.inv_deg, self.has_in, ws, _lib.size_t(ws.numel()),
+                      _lib.stream_ptr(torch.cuda.current_stream(dev)))
+
+
+# ------------------------------------------------------------------------------------------ collectives (NCCL or gloo)
+def all_gather_rows(local_padded, world, group=None):
+    """[max_rows, C] per rank -> [world * max_rows, C] (rank-major), same on every rank."""
+    out = local_padded.new_empty((world * local_padded.shape[0],) + tuple(local_padded.shape[1:]))
+    if dist.get_backend(group) == "gloo":
+        parts = list(out.chunk(world, dim=0))
+        dist.all_gather(parts, local_padded.contiguous(), group=group)
+    else:
+        dist.all_gather_into_tensor(out, local_padded.contiguous(), group=group)
+    return out
+
+
+def reduce_scatter_rows(partial, world, rank, group=None):
+    """[world * max_rows, C] partial sums per rank -> [max_rows, C]: the sum over ranks of this rank's chunk."""
+    rows = partial.shape[0] // world
+    if dist.get_backend(group) == "gloo":
+        full = partial.clone()
+        dist.all_reduce(full, group=group)
+        return full[rank * rows:(rank + 1) * rows].contiguous()
+    out = partial.new_empty((rows,) + tuple(partial.shape[1:]))
+    dist.reduce_scatter_tensor(out, partial.contiguous(), group=group)
+    return out
+
+
+# ------------------------------------------------------------------------------------------ the layer
+class _DistAMPConvFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_local, w_in, b_in, w_out, b_out, pg, num_heads, group):
+        dev = x_local.device
+        g = pg.device_graph()
+        n, width = x_local.shape
+        d = w_in.shape[1]
+        f = width // d
+        hd = d // num_heads
+        world, max_n = pg.world, pg.max_n
+        rows, prow = n * f, max_n * f
+        with torch.cuda.device(dev):
+            st = F_._stream(dev)
+            ws = torch.zeros(64, dtype=torch.int32, device=dev)
+            q = torch.empty((rows, d), dtype=torch.bfloat16, device=dev)
+            kv_local = torch.zeros((2, prow, d), dtype=torch.bfloat16, device=dev)    # padded rows stay zero
+            _lib.call("ampconv_qkv_proj_tc", x_local, w_in, b_in, q, kv_local[0], kv_local[1], _lib.i64(rows), _lib.i32(d),
+                      _lib.f32(F_.LOG2E / hd ** 0.5), ws, st)
+            k_all = all_gather_rows(kv_local[0], world, group)
+            v_all = all_gather_rows(kv_local[1], world, group)
+            agg = torch.empty((rows, d), dtype=torch.float32, device=dev)
+            lse2 = torch.empty((g.num_edges, num_heads, (f + 3) // 4 * 4), dtype=torch.float32, device=dev)
+            out = torch.empty((n, width), dtype=torch.float32, device=dev)
+            _lib.call("ampconv_attn_fwd_bf16_part", q, k_all, v_all, g.dst_rowptr, g.dst_src, g.inv_deg, agg, lse2,
+                      _lib.i64(n), _lib.i64(pg.num_kv_nodes), _lib.i64(g.num_edges), _lib.i32(f), _lib.i32(d),
+                      _lib.i32(num_heads), ws, _lib.size_t(256), st)
+            _lib.call("ampconv_out_proj_tc", agg, w_out, b_out, g.has_in, out, _lib.i64(n), _lib.i32(f), _lib.i32(d), ws, st)
+        ctx.save_for_backward(x_local, w_in, w_out)
+        ctx.state = (pg, group, num_heads, q, k_all, v_all, agg, lse2, ws)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x_local, w_in, w_out = ctx.saved_tensors
+        pg, group, h, q, k_all, v_all, agg, lse2, bws = ctx.state
+        g = pg.device_graph()
+        dev = x_local.device
+        n, width = x_local.shape
+        d = w_in.shape[1]
+        f = width // d
+        rows, prow = n * f, pg.max_n * f
+        e = g.num_edges
+        with torch.cuda.device(dev):
+            st = F_._stream(dev)
+            d_out = d_out.contiguous()
+            d_agg = torch.empty((rows, d), dtype=torch.bfloat16, device=dev)
+            d_w_out = torch.empty_like(w_out)
+            d_b_out = torch.empty(d, dtype=torch.float32, device=dev)
+            ws = F_._param_grad_ws(3 * d, d, dev)
+            _lib.call("ampconv_out_proj_bwd_input_tc", d_out, w_out, g.inv_deg, d_agg, _lib.i64(n), _lib.i32(f), _lib.i32(d),
+                      bws, st)
+            _lib.call("ampconv_out_proj_bwd_params_tc", d_out, agg, g.has_in, d_w_out, d_b_out, _lib.i64(n), _lib.i32(f),
+                      _lib.i32(d), ws, _lib.size_t(ws.numel()), bws, st)
+            d_q = torch.empty((rows, d), dtype=torch.float32, device=dev)
+            delta = torch.empty_like(lse2)
+            tail = (_lib.i64(n), _lib.i64(pg.num_kv_nodes), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(h), bws,
+                    _lib.size_t(256), st)
+            _lib.call("ampconv_attn_bwd_dq_bf16_part", q, k_all, v_all, d_agg, lse2, g.dst_rowptr, g.dst_src, d_q, delta, *tail)
+            d_kv_partial = torch.empty((pg.num_kv_nodes * f, 2 * d), dtype=torch.float32, device=dev)
+            _lib.call("ampconv_attn_bwd_dkv_bf16_part", q, k_all, v_all, d_agg, lse2, delta, g.src_rowptr, g.src_dst,
+                      g.src_pos, d_kv_partial, *tail)
+            d_kv = reduce_scatter_rows(d_kv_partial, pg.world, pg.rank, group)        # [max_n * F, 2d], rows >= n*F are padding
+            del d_kv_partial
+            d_qkv = torch.cat([d_q, d_kv[:rows]], dim=1)
+            d_x = torch.empty_like(x_local)
+            d_w_in = torch.empty_like(w_in)
+            d_b_in = torch.empty(3 * d, dtype=torch.float32, device=dev)
+            _lib.call("ampconv_qkv_proj_bwd_input_tc", d_qkv, w_in, d_x, _lib.i64(rows), _lib.i32(d), bws, st)
+            _lib.call("ampconv_qkv_proj_bwd_params_tc", x_local, d_qkv, d_w_in, d_b_in, _lib.i64(rows), _lib.i32(d), ws,
+                      _lib.size_t(ws.numel()), bws, st)
+            flat = torch.cat([d_w_in.flatten(), d_b_in, d_w_out.flatten(), d_b_out])
+            dist.all_reduce(flat, group=group)
+            o = 0
+            outs = []
+            for t in (d_w_in, d_b_in, d_w_out, d_b_out):
+                outs.append(flat[o:o + t.numel()].view_as(t))
+                o += t.numel()
+        return d_x, outs[0], outs[1], outs[2], outs[3], None, None, None
+
+
+def dist_amp_conv(x_local, pg, w_in, b_in, w_out, b_out, num_heads, group=None):
+    """AMPConv forward for the rows this rank owns (x_local = x[lo:hi]); differentiable; bf16 (tcgen05) family only."""
+    d = w_in.shape[1]
+    f = x_local.shape[1] // d
+    if not F_.bf16_supported(f, d, num_heads):
+        raise ValueError("the partitioned path uses the tcgen05 family: embed_dim 64, head_dim 16 or 32, F <= 128")
+    return _DistAMPConvFunction.apply(x_local.contiguous(), w_in, b_in, w_out, b_out, pg, num_heads, group)

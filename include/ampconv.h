@@ -75,6 +75,15 @@ AMPCONV_API int ampconv_graph_build(const int64_t* edge_index /* [2,E] row 0 = s
                         float* inv_deg, float* has_in,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same for a destination-partitioned graph (multi-GPU): destinations are local ids in [0, num_nodes), sources
+ * are ids in [0, num_src_nodes) of the all-gathered K/V tensors; src_rowptr has num_src_nodes + 1 entries. */
+AMPCONV_API int ampconv_graph_build_bipartite(const int64_t* edge_index, int64_t num_edges, int64_t num_nodes,
+                                  int64_t num_src_nodes,
+                                  int32_t* dst_rowptr, int32_t* dst_src, int32_t* dst_eid,
+                                  int32_t* src_rowptr, int32_t* src_dst, int32_t* src_pos,
+                                  float* inv_deg, float* has_in,
+                                  void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Strict fp32 family (CUDA cores, any F / d / H with hd <= 128).  Parity bar 1e-4 relative.
  * ------------------------------------------------------------------------------------------ */
@@ -182,6 +191,9 @@ AMPCONV_API int ampconv_attn_fwd_bf16_profile(const void* q, const void* k, cons
                                   int64_t num_nodes, int64_t num_edges, int F, int d, int H,
                                   void* workspace, size_t workspace_bytes, void* stream, long long* prof);
 
+/* Debug: device buffer of 9 int64 (or NULL) that makes the tcgen05 backward kernels record per-phase cycles. */
+AMPCONV_API int ampconv_debug_set_bwd_profile(long long* prof);
+
 /* Backward of ampconv_out_proj_f32 for the bf16 family: identical, except that d_agg (already
  * multiplied by inv_deg) is emitted as bf16 [N,F,d], the dO tile the tcgen05 backward kernels load. */
 AMPCONV_API int ampconv_out_proj_bwd_bf16(const float* d_out, const float* agg, const float* out_proj_weight,
@@ -233,6 +245,24 @@ AMPCONV_API int ampconv_out_proj_bwd_params_tc(const float* d_out, const float* 
 AMPCONV_API int ampconv_qkv_proj_bwd_params_tc(const float* x, const float* d_qkv, float* d_w, float* d_b,
                                    int64_t rows, int d, void* scratch, size_t scratch_bytes, void* workspace,
                                    void* stream);
+
+/* Destination-partitioned variants of the three attention kernels (multi-GPU): q / d_agg cover the
+ * num_nodes LOCAL destinations, k / v the num_kv_nodes rows of the all-gathered K / V; graph views come from
+ * ampconv_graph_build_bipartite.  _dq writes d_q fp32 [num_nodes*F, d]; _dkv writes the partial d_k | d_v
+ * fp32 [num_kv_nodes*F, 2d] contributed by the local edges (the host reduce-scatters it to the owners). */
+AMPCONV_API int ampconv_attn_fwd_bf16_part(const void* q, const void* k, const void* v,
+                               const int32_t* dst_rowptr, const int32_t* dst_src, const float* inv_deg,
+                               float* agg, float* lse2, int64_t num_nodes, int64_t num_kv_nodes, int64_t num_edges,
+                               int F, int d, int H, void* workspace, size_t workspace_bytes, void* stream);
+AMPCONV_API int ampconv_attn_bwd_dq_bf16_part(const void* q, const void* k, const void* v, const void* d_agg_bf16,
+                                  const float* lse2, const int32_t* dst_rowptr, const int32_t* dst_src,
+                                  float* d_q, float* delta, int64_t num_nodes, int64_t num_kv_nodes, int64_t num_edges,
+                                  int F, int d, int H, void* workspace, size_t workspace_bytes, void* stream);
+AMPCONV_API int ampconv_attn_bwd_dkv_bf16_part(const void* q, const void* k, const void* v, const void* d_agg_bf16,
+                                   const float* lse2, const float* delta, const int32_t* src_rowptr,
+                                   const int32_t* src_dst, const int32_t* src_pos, float* d_kv,
+                                   int64_t num_nodes, int64_t num_kv_nodes, int64_t num_edges, int F, int d, int H,
+                                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* Copies the status word of the last bf16 kernel that used `workspace` to the host (0 = ok, otherwise
  * the id of the pipeline wait that timed out).  Synchronises `stream`; meant for tests and debugging. */

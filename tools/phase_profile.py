@@ -36,5 +36,45 @@ def main():
     if p[15] > 0: print(f"MMA thread: items={mi} total/item={p[12] / mi:.0f} issue-QK/item={p[13] / mi:.0f} issue-PV/item={p[14] / mi:.0f} "
           f"idle/item={(p[12] - p[13] - p[14]) / mi:.0f}")
 
+def bwd():
+    dev = torch.device("cuda:0")
+    n, e, f, d, h = 16934, 116624, 128, 64, 4
+    ei = torch.from_numpy(cases.make_graph("uniform", n, e, seed=7)).to(dev)
+    g = Graph(ei, n)
+    rows = n * f
+    q = torch.randn(rows, d, device=dev).to(torch.bfloat16) * 0.5
+    k = torch.randn(rows, d, device=dev).to(torch.bfloat16)
+    v = torch.randn(rows, d, device=dev).to(torch.bfloat16)
+    do = torch.randn(rows, d, device=dev).to(torch.bfloat16)
+    agg = torch.empty(rows, d, device=dev)
+    lse2 = torch.empty(e, h, f, device=dev)
+    delta = torch.empty(e, h, f, device=dev)
+    dqkv = torch.empty(rows, 3 * d, device=dev)
+    ws = torch.zeros(64, dtype=torch.int32, device=dev)
+    st = _lib.stream_ptr(torch.cuda.current_stream(dev))
+    tail = (_lib.i64(n), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(h), ws, _lib.size_t(256), st)
+    _lib.call("ampconv_attn_fwd_bf16", q, k, v, g.dst_rowptr, g.dst_src, g.inv_deg, None, agg, lse2, *tail)
+    prof = torch.zeros(16, dtype=torch.int64, device=dev)
+    lib = _lib.load()
+    names = ["wait X/Y", "chunks (ld, exp, pack, st)", "publish", "wait T", "fold T", "stats/lse load", "node wait", "node epilogue"]
+    for mode in ("dq", "dkv"):
+        prof.zero_()
+        lib.ampconv_debug_set_bwd_profile(ctypes.c_void_p(prof.data_ptr()))
+        if mode == "dq":
+            _lib.call("ampconv_attn_bwd_dq_bf16", q, k, v, do, lse2, g.dst_rowptr, g.dst_src, dqkv, delta, *tail)
+        else:
+            _lib.call("ampconv_attn_bwd_dkv_bf16", q, k, v, do, lse2, delta, g.src_rowptr, g.src_dst, g.src_pos, dqkv, *tail)
+        torch.cuda.synchronize()
+        lib.ampconv_debug_set_bwd_profile(ctypes.c_void_p(0))
+        p = prof.cpu().tolist()
+        items = max(1, p[8])
+        tot = sum(p[:8])
+        print(f"bwd {mode}: items={items} total cycles/item={tot / items:.0f}")
+        for nm, cyc in zip(names, p[:8]):
+            print(f"  {nm:28s} {cyc / items:8.1f} cyc/item  {100.0 * cyc / tot:5.1f}%")
+
+
 if __name__ == "__main__":
+    import ctypes
+    bwd()
     main()
