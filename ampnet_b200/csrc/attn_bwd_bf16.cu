@@ -14,9 +14,10 @@
 //
 // Work split: an item = (edge, head).  Its two score tiles X, Y live in one of two TMEM sets (item parity:
 // columns [256s, 256s+256), X at +0, Y at +128), so the score MMAs of item c+1 run while item c is being
-// processed.  All 8 elementwise warps work on the same item: warpgroup b owns score columns [64b, 64b+64)
-// of every row; the bf16 operands P / W (or P^T / dS^T) overwrite the fp32 scores in place (packed columns
-// +0..31 for score columns 0..63, +64..95 for 64..127); TX / TY land in columns +32.. of X / Y.
+// processed.  All 16 elementwise warps work on the same item (4 per SM sub-partition, to hide tcgen05.ld and
+// MUFU latency): warp w owns TMEM lane quarter w & 3 and score columns [32g, 32g+32), g = w >> 2.  The bf16
+// operands P / W (or P^T / dS^T) overwrite the first 16 columns of each group's own fp32 scores in place, so a
+// write can never pass another warp's read; TX / TY land in the 16-column holes at +16 (and +48 for hd = 32).
 // tcgen05 issue costs ~100 clk per instruction, so three converged warps issue: X/Y, TX and TY.
 #include <cuda_bf16.h>
 #include <math_constants.h>
@@ -31,7 +32,8 @@ using namespace umma;
 
 constexpr int kD = 64;
 constexpr int kTileBytes = 128 * 128;
-constexpr int kThreads = 384;   // 2 elementwise warpgroups + producer warp + 3 MMA-issuing warps
+constexpr int kEwWarps = 16;     // elementwise warps: 4 TMEM lane quarters x 4 column groups of 32 score columns
+constexpr int kThreads = (kEwWarps + 4) * 32;   // + producer warp + 3 MMA-issuing warps
 constexpr int MODE_DQ = 0, MODE_DKV = 1;
 constexpr int kStatFloats = 4 * 128;   // H * roundup4(F) <= 512 floats per edge and statistic
 
@@ -46,11 +48,11 @@ struct BwdSmem {
   uint8_t own[2][2][kTileBytes];        // [slot][tile 0/1]
   uint8_t edge[NS][2][kTileBytes];      // [stage][tile 0/1]
   float stat[NS][2][kStatFloats];       // MODE_DKV: lse2 / delta rows of the edge
-  float acc[NACC * 32][256];
+  float acc[NACC * 16][512];            // [accumulator element][elementwise thread]
   uint64_t own_full[2], own_empty[2];
   uint64_t edge_full[NS], edge_empty[NS];
   uint64_t xy_full[2], xy_empty[2], u_full[2], t_full[2];
-  float dl[2][2][128];                  // MODE_DQ: partial delta of [set][warpgroup][row]
+  float dl[2][4][128];                  // MODE_DQ: partial delta of [set][column group][row]
   NodeSlot slot[2];
   uint32_t tmem_base;
 };
@@ -91,23 +93,23 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Fs = (F + 3) & ~3;   // row stride of the statistics arrays
 
-  if (warp == 9) tmem_alloc(&sm.tmem_base, 512);
+  if (warp == kEwWarps + 1) tmem_alloc(&sm.tmem_base, 512);
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sm.own_full[i], 1);
-      mbar_init(&sm.own_empty[i], 1 + 8 + 2);
+      mbar_init(&sm.own_empty[i], 1 + kEwWarps + 2);
       mbar_init(&sm.xy_full[i], 1);
-      mbar_init(&sm.xy_empty[i], 8);
-      mbar_init(&sm.u_full[i], 8);
+      mbar_init(&sm.xy_empty[i], kEwWarps);
+      mbar_init(&sm.u_full[i], kEwWarps);
       mbar_init(&sm.t_full[i], 2);
     }
     for (int i = 0; i < NS; ++i) {
       mbar_init(&sm.edge_full[i], 1);
-      mbar_init(&sm.edge_empty[i], MODE == MODE_DKV ? 3 + 8 : 3);
+      mbar_init(&sm.edge_empty[i], MODE == MODE_DKV ? 3 + kEwWarps : 3);
     }
     fence_barrier_init();
   }
-  if (warp == 8 && lane == 0) {
+  if (warp == kEwWarps && lane == 0) {
     prefetch_tensormap(&own0);
     prefetch_tensormap(&own1);
     prefetch_tensormap(&oth0);
@@ -121,7 +123,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
   const int ksteps = (F + 15) >> 4;
   const uint32_t stat_bytes = (uint32_t)(H * Fs * sizeof(float));
 
-  if (warp == 8) {
+  if (warp == kEwWarps) {
     // ------------------------------------------------------------------ producer / scheduler
     uint32_t qi = 0, ei = 0;
     for (;;) {
@@ -193,7 +195,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       if (failed) AMP_FAIL(failed);
       if (node < 0) break;
     }
-  } else if (warp == 9) {
+  } else if (warp == kEwWarps + 1) {
     // ------------------------------------------------------------------ score MMAs X, Y of every item
     {
       const uint32_t idesc_xy = idesc_bf16(128, nqk, 0, 0);
@@ -229,12 +231,12 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
         }
       }
     }
-  } else if (warp >= 10) {
-    // ------------------------------------------------------------------ T MMAs: warp 10 issues TX = X' * B_tx, warp 11 TY = Y' * B_ty
+  } else if (warp >= kEwWarps + 2) {
+    // ------------------------------------------------------------------ T MMAs: one warp issues TX = X' * B_tx, the other TY = Y' * B_ty
     //   (A = the bf16 operand the elementwise warps wrote back into TMEM, B = an edge tile as MN-major operand)
     {
-      const uint32_t which = warp - 10;                       // 0: TX, 1: TY
-      const uint32_t idesc_t = idesc_bf16(128, HD, 0, 1);
+      const uint32_t which = warp - (kEwWarps + 2);            // 0: TX, 1: TY
+      const uint32_t idesc_t = idesc_bf16(128, 16, 0, 1);      // N = 16 per MMA (two per K step when hd = 32)
       const int btile = (which == 0 && MODE == MODE_DKV) ? 1 : 0;   // TX of the dK/dV pass multiplies dO; all others tile 0
       uint32_t qi = 0, edge = 0, c = 0;
       for (;; ++qi) {
@@ -255,8 +257,12 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
             const uint64_t bd = smem_desc(smem_u32(sm.edge[st][btile]) + h * (HD * 2), 16, 1024, LAYOUT_SW128);
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)
-              if (ks < ksteps)
-                mma_ts_w(a_col + 32, a_col + (ks < 4 ? 8 * ks : 64 + 8 * (ks - 4)), desc_advance(bd, ks * 2048), idesc_t, ks > 0);
+              if (ks < ksteps) {
+                const uint32_t a_addr = a_col + 32 * (ks >> 1) + 8 * (ks & 1);
+#pragma unroll
+                for (int half = 0; half < HD / 16; ++half)
+                  mma_ts_w(a_col + 16 + 32 * half, a_addr, desc_advance(bd, ks * 2048 + half * 32), idesc_t, ks > 0);
+              }
             mma_commit_w(&sm.t_full[set]);
           }
           mma_commit_w(&sm.edge_empty[st]);
@@ -264,14 +270,14 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       }
     }
   } else {
-    // ------------------------------------------------------------------ elementwise warps: warpgroup b owns score columns [64b, 64b+64)
-    const uint32_t b = warp >> 2;
+    // ------------------------------------------------------------------ elementwise warps
+    const uint32_t g = warp >> 2;                   // column group: score columns [32g, 32g+32)
     const int row = (warp & 3) * 32 + lane;
     const bool row_ok = row < F;
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    constexpr int HH = HD / 2;                      // T columns this thread reads back per head
+    constexpr int HQ = HD / 4;                      // T columns this thread reads back per head
     uint32_t qi = 0, c = 0, ei = 0;
-    float* acc = &sm.acc[0][b * 128 + row];         // element x of this thread: acc[x * 256]
+    float* acc = &sm.acc[0][threadIdx.x];           // element x of this thread: acc[x * 512]
     const bool do_prof = PROF && blockIdx.x == 0;
     long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tp = do_prof ? clock64() : 0;
@@ -285,40 +291,43 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       if (lane == 0) mbar_arrive(&sm.own_empty[qb]);
       if (ns.node < 0) break;
 #pragma unroll
-      for (int x = 0; x < Smem::NACC * H * HH; ++x) acc[x * 256] = 0.f;
+      for (int x = 0; x < Smem::NACC * H * HQ; ++x) acc[x * 512] = 0.f;
       uint32_t t = 0;
       int e_prev = 0;
-      // folds this thread's half of TX / TY of item cc (head hp, edge slot ep) into the accumulators, frees the set
+      // folds this thread's HQ columns of TX / TY of item cc (head hp, edge slot ep) into the accumulators, frees the set
       auto readback = [&](uint32_t cc, int hp, int ep) -> bool {
         const uint32_t set = cc & 1;
         if (!mbar_wait(&sm.t_full[set], (cc >> 1) & 1)) return false;
         AMP_PHASE(3);
         tc_fence_after();
-        uint32_t tx[HH], ty[HH];
-        const uint32_t base = lane_base + set * 256 + 32 + HH * b;
-        if constexpr (HH == 8) {
+        uint32_t tx[HQ], ty[HQ];
+        // logical T column HQ*g maps to +16 + col (hd = 16) or to the two 16-column holes +16 / +48 (hd = 32)
+        const uint32_t tcol = HQ * g;
+        const uint32_t base = lane_base + set * 256 + (tcol < 16 ? 16 + tcol : 48 + (tcol - 16));
+        if constexpr (HQ == 4) {
+          tmem_ld_32x32b_x4(base, tx);
+          tmem_ld_32x32b_x4(base + 128, ty);
+        } else {
           tmem_ld_32x32b_x8(base, tx);
           tmem_ld_32x32b_x8(base + 128, ty);
-        } else {
-          tmem_ld_32x32b_x16(base, tx);
-          tmem_ld_32x32b_x16(base + 128, ty);
         }
         tmem_ld_wait();
-        const float dl = (MODE == MODE_DQ) ? sm.dl[set][0][row] + sm.dl[set][1][row] : 0.f;   // before the set is released
+        float dl = 0.f;
+        if (MODE == MODE_DQ) dl = (sm.dl[set][0][row] + sm.dl[set][1][row]) + (sm.dl[set][2][row] + sm.dl[set][3][row]);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.xy_empty[set]);
-        float* a = acc + hp * HH * 256;
+        float* a = acc + hp * HQ * 512;
         if (MODE == MODE_DQ) {
-          if (b == 0 && row_ok) delta[((int64_t)ep * H + hp) * Fs + row] = dl;
+          if (g == 0 && row_ok) delta[((int64_t)ep * H + hp) * Fs + row] = dl;
 #pragma unroll
-          for (int x = 0; x < HH; ++x) a[x * 256] += __uint_as_float(ty[x]) - dl * __uint_as_float(tx[x]);
+          for (int x = 0; x < HQ; ++x) a[x * 512] += __uint_as_float(ty[x]) - dl * __uint_as_float(tx[x]);
         } else {
-          float* a2 = a + H * HH * 256;
+          float* a2 = a + H * HQ * 512;
 #pragma unroll
-          for (int x = 0; x < HH; ++x) {
-            a[x * 256] += __uint_as_float(ty[x]);    // dK
-            a2[x * 256] += __uint_as_float(tx[x]);   // dV
+          for (int x = 0; x < HQ; ++x) {
+            a[x * 512] += __uint_as_float(ty[x]);    // dK
+            a2[x * 512] += __uint_as_float(tx[x]);   // dV
           }
         }
         AMP_PHASE(4);
@@ -338,19 +347,19 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
           tc_fence_after();
           const float* Ls = sm.stat[st][0] + h * Fs;
           const float* Ds = sm.stat[st][1] + h * Fs;
-          const uint32_t xbase = lane_base + set * 256;
+          const uint32_t xbase = lane_base + set * 256 + 32 * g;
           float dl0 = 0.f, dl1 = 0.f;
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
-            const int col0 = 64 * b + 32 * k;          // first score column of this chunk
+            const int col0 = 32 * g + 16 * k;          // first score column of this sub-chunk
             if (col0 < nqk) {
-              uint32_t xs[32], ys[32];
-              tmem_ld_32x32b_x32(xbase + col0, xs);
-              tmem_ld_32x32b_x32(xbase + 128 + col0, ys);
+              uint32_t xs[16], ys[16];
+              tmem_ld_32x32b_x16(xbase + 16 * k, xs);
+              tmem_ld_32x32b_x16(xbase + 128 + 16 * k, ys);
               tmem_ld_wait();
-              uint32_t px[16], py[16];
+              uint32_t px[8], py[8];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
+              for (int j = 0; j < 8; ++j) {
                 const int c0 = col0 + 2 * j;
                 float p0, p1, u0, u1;
                 if (MODE == MODE_DQ) {
@@ -375,12 +384,12 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
                 px[j] = pack_bf16x2(p0, p1);
                 py[j] = pack_bf16x2(u0, u1);
               }
-              // packed columns: score columns 0..63 -> +0..31, 64..127 -> +64..95 (always behind this thread's own reads)
-              tmem_st_32x32b_x16(xbase + 64 * b + 16 * k, px);
-              tmem_st_32x32b_x16(xbase + 128 + 64 * b + 16 * k, py);
+              // packed columns +8k of this group's own 32 columns: always behind this thread's own reads
+              tmem_st_32x32b_x8(xbase + 8 * k, px);
+              tmem_st_32x32b_x8(xbase + 128 + 8 * k, py);
             }
           }
-          if (MODE == MODE_DQ) sm.dl[set][b][row] = dl0 + dl1;
+          if (MODE == MODE_DQ) sm.dl[set][g][row] = dl0 + dl1;
           AMP_PHASE(1);
           tmem_st_wait();
           tc_fence_before();
@@ -406,19 +415,19 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
         float* o = d_qkv + ((int64_t)ns.node * F + row) * out_ld;
 #pragma unroll
         for (int h = 0; h < H; ++h) {
-          const float* a = acc + h * HH * 256;
-          float4* o0 = reinterpret_cast<float4*>(o + out_c0 + h * HD + HH * b);
+          const float* a = acc + h * HQ * 512;
+          float4* o0 = reinterpret_cast<float4*>(o + out_c0 + h * HD + HQ * g);
 #pragma unroll
-          for (int x = 0; x < HH; x += 4)
-            o0[x >> 2] = make_float4(a[x * 256] * out_scale0, a[(x + 1) * 256] * out_scale0,
-                                     a[(x + 2) * 256] * out_scale0, a[(x + 3) * 256] * out_scale0);
+          for (int x = 0; x < HQ; x += 4)
+            o0[x >> 2] = make_float4(a[x * 512] * out_scale0, a[(x + 1) * 512] * out_scale0,
+                                     a[(x + 2) * 512] * out_scale0, a[(x + 3) * 512] * out_scale0);
           if (MODE == MODE_DKV) {
-            const float* a2 = a + H * HH * 256;
-            float4* o1 = reinterpret_cast<float4*>(o + out_c1 + h * HD + HH * b);
+            const float* a2 = a + H * HQ * 512;
+            float4* o1 = reinterpret_cast<float4*>(o + out_c1 + h * HD + HQ * g);
 #pragma unroll
-            for (int x = 0; x < HH; x += 4)
-              o1[x >> 2] = make_float4(a2[x * 256] * out_scale1, a2[(x + 1) * 256] * out_scale1,
-                                       a2[(x + 2) * 256] * out_scale1, a2[(x + 3) * 256] * out_scale1);
+            for (int x = 0; x < HQ; x += 4)
+              o1[x >> 2] = make_float4(a2[x * 512] * out_scale1, a2[(x + 1) * 512] * out_scale1,
+                                       a2[(x + 2) * 512] * out_scale1, a2[(x + 3) * 512] * out_scale1);
           }
         }
       }
@@ -434,7 +443,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
 fail:
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem, 512);
+  if (warp == kEwWarps + 1) tmem_dealloc(tmem, 512);
 }
 
 long long* g_bwd_prof = nullptr;   // debug: set through ampconv_debug_set_bwd_profile

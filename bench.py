@@ -193,7 +193,8 @@ def run_ours(args):
     spec = dict(WORKLOADS[args.workload])
     n, e, f, d, h = spec["n"], spec["e"], spec["f"], spec["d"], spec["h"]
 
-    # every rank owns an independent graph shard of the workload's shape (weak scaling; see DESIGN.md "Multi-GPU")
+    if world > 1:
+        return run_ours_partitioned(args, spec, world, rank, dev)
     edge_index_np = make_problem(spec, args.graph, seed=rank)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     x_host = torch.empty((n, f * d), dtype=torch.float32, pin_memory=True)
@@ -316,6 +317,108 @@ def run_ours(args):
     print(json.dumps(line))
 
 
+def run_ours_partitioned(args, spec, world, rank, dev):
+    """N > 1: the SAME graph, destination-partitioned over the ranks (strong scaling); K/V all-gather forward,
+    dK/dV reduce-scatter and parameter-gradient all-reduce backward (ampnet_b200/distributed.py)."""
+    import torch.distributed as dist
+    from ampnet_b200 import AMPConv, _lib, distributed as D
+    n, e, f, d, h = spec["n"], spec["e"], spec["f"], spec["d"], spec["h"]
+    edge_index_np = make_problem(spec, args.graph, seed=0)            # identical on every rank
+    ei_host = torch.from_numpy(edge_index_np).pin_memory()
+    edge_index = ei_host.to(dev)
+    pg = D.PartitionedGraph(edge_index, n, world, rank)
+    pg.device_graph()
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = torch.randn((pg.n_local, f * d), generator=gen, device=dev)
+    d_out = torch.randn((pg.n_local, f * d), generator=gen, device=dev)
+    x_host = torch.empty_like(x, device="cpu").pin_memory()
+    x_host.copy_(x)
+    conv = AMPConv(d, h, mode="bf16").to(dev)
+    init_conv(conv)
+    mha = conv.multi_head_attention
+    params = list(conv.parameters())
+
+    def step(xin):
+        for p in params:
+            p.grad = None
+        xin.grad = None
+        out = D.dist_amp_conv(xin, pg, mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight, mha.out_proj.bias, h)
+        loss = (out * d_out).sum()
+        loss.backward()
+        return loss
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    x.requires_grad_(True)
+    for _ in range(args.warmup):
+        step(x)
+    barrier()
+    launches0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(dev.index) as clocks:
+        ev0.record()
+        for _ in range(args.steps):
+            step(x)
+        ev1.record()
+        barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    launches = (_lib.launch_count() - launches0) // max(1, args.steps)
+
+    # end to end: H2D of this rank's rows of x from pinned memory, fwd, bwd, D2H of loss and parameter gradients
+    x_dev = torch.empty_like(x_host, device=dev)
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    grads_host = [torch.empty_like(p, device="cpu").pin_memory() for p in params]
+
+    def e2e_step():
+        x_dev.copy_(x_host, non_blocking=True)
+        xin = x_dev.detach().requires_grad_(True)
+        loss = step(xin)
+        loss_host.copy_(loss.detach(), non_blocking=True)
+        for gh, p in zip(grads_host, params):
+            gh.copy_(p.grad, non_blocking=True)
+
+    e2e_step()
+    barrier()
+    e2e_steps = max(1, min(args.steps, 3))
+    ev0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    ev1.record()
+    barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1) / e2e_steps], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    sizes = torch.tensor([x_host.numel() * 4, 4 + sum(p.numel() * 4 for p in params)], device=dev, dtype=torch.float64)
+    dist.all_reduce(sizes)
+    if rank != 0:
+        return
+    pk = peaks()
+    line = {
+        "metric": METRIC, "value": e / (ms_step * 1e-3), "unit": "edges/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {spec['desc']} (N={n}, E={e}, F={f}, d={d}, H={h}), one AMPConv layer "
+                               f"fwd+bwd, {args.graph} graph seed 7", "mode": "bf16",
+                   "l2": "inputs larger than L2; no flush",
+                   "parallelism": f"dst-partitioned over {world} GPUs: all-gather K|V (bf16), reduce-scatter dK|dV (fp32), "
+                                  "all-reduce parameter gradients (NCCL)"},
+        "node_updates_per_s": n / (ms_step * 1e-3),
+        "clocks": clocks.summary(),
+        "e2e": {"value": e / (e2e_ms * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": int(sizes[0].item()),
+                "d2h_bytes_per_step": int(sizes[1].item()), "ms_per_step": e2e_ms,
+                "includes": "H2D of every rank's rows of x from pinned memory, fwd, bwd (with the collectives), D2H of loss and 4 "
+                            "param grads; the partitioned CSR is built once (static graph)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "whole step (see the N=1 line for per-kernel numbers)", "achieved": None,
+                     "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": None, "traffic": None, "peak_source": pk["source"]},
+    }
+    print(json.dumps(line))
+
+
 def profile_attention_kernels(conv, x, edge_index, d_out, mode, reps):
     """Times each attention kernel alone with CUDA events on the stream it is launched on."""
     from ampnet_b200 import _lib
@@ -338,7 +441,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
     ap.add_argument("--graph", default="uniform", choices=["uniform", "skewed"])
-    ap.add_argument("--mode", default=os.environ.get("AMPNET_B200_BENCH_MODE", "fp32"))
+    ap.add_argument("--mode", default=os.environ.get("AMPNET_B200_BENCH_MODE", "bf16"))
     ap.add_argument("--cpu-sample-edges", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -348,6 +451,9 @@ def main():
         run_reference(args)
     else:
         run_ours(args)
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":
