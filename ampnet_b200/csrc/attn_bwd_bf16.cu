@@ -388,6 +388,11 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
               tmem_st_32x32b_x8(xbase + 8 * k, px);
               tmem_st_32x32b_x8(xbase + 128 + 8 * k, py);
             }
+            // Half way through the item the previous item's T tiles are complete: fold them in now and release its
+            // TMEM set, so that the score MMAs of the next item are issued while the second sub-chunk is processed.
+            if (k == 0 && t > 0) {
+              if (!readback(c - 1, (h + H - 1) % H, e_prev)) AMP_FAIL(304);
+            }
           }
           if (MODE == MODE_DQ) sm.dl[set][g][row] = dl0 + dl1;
           AMP_PHASE(1);
@@ -399,10 +404,6 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
             if (lane == 0) mbar_arrive(&sm.edge_empty[st]);   // this warp no longer reads the stage's statistics rows
           }
           AMP_PHASE(2);
-          // the previous item's T tiles are complete by now: fold them in and release its set for the score MMAs
-          if (t > 0) {
-            if (!readback(c - 1, (h + H - 1) % H, e_prev)) AMP_FAIL(304);
-          }
           e_prev = e;
           ++c;
           ++t;
