@@ -444,10 +444,11 @@ extern "C" int ampconv_attn_fwd_bf16_profile(const void* q, const void* k, const
 // the all-gathered tensors; dst_src holds ids into k / v.
 extern "C" int ampconv_attn_fwd_bf16_part(const void* q, const void* k, const void* v,
                                           const int32_t* dst_rowptr, const int32_t* dst_src, const float* inv_deg,
-                                          float* agg, float* lse2, int64_t num_nodes, int64_t num_kv_nodes, int64_t E,
+                                          const int32_t* order, float* agg, float* lse2, int64_t num_nodes,
+                                          int64_t num_kv_nodes, int64_t E,
                                           int F, int d, int H, void* workspace, size_t workspace_bytes, void* stream_) {
   AMPCONV_REQUIRE(num_kv_nodes > 0 || E == 0);
-  return attn_fwd_bf16_impl(q, k, v, dst_rowptr, dst_src, inv_deg, nullptr, agg, lse2, num_nodes,
+  return attn_fwd_bf16_impl(q, k, v, dst_rowptr, dst_src, inv_deg, order, agg, lse2, num_nodes,
                             num_kv_nodes > 0 ? num_kv_nodes : 1, E, F, d, H, workspace, workspace_bytes, stream_, nullptr);
 }
 

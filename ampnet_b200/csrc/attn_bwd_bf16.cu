@@ -33,7 +33,8 @@ using namespace umma;
 constexpr int kD = 64;
 constexpr int kTileBytes = 128 * 128;
 constexpr int kEwWarps = 16;     // elementwise warps: 4 TMEM lane quarters x 4 column groups of 32 score columns
-constexpr int kThreads = (kEwWarps + 4) * 32;   // + producer warp + 3 MMA-issuing warps
+constexpr int kTWarps = 4;       // T-MMA issuing warps: (TX | TY) x (K steps 0-3 | 4-7)
+constexpr int kThreads = (kEwWarps + 2 + kTWarps) * 32;   // + producer warp + score-MMA warp + T warps
 constexpr int MODE_DQ = 0, MODE_DKV = 1;
 constexpr int kStatFloats = 4 * 128;   // H * roundup4(F) <= 512 floats per edge and statistic
 
@@ -81,8 +82,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_constant__ CUtensorMap own1,
                      const __grid_constant__ CUtensorMap oth0, const __grid_constant__ CUtensorMap oth1,
                      const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr,
-                     const int32_t* __restrict__ slot_of, const float* __restrict__ lse2, float* __restrict__ delta,
-                     float* __restrict__ d_qkv, int* __restrict__ counter, int* __restrict__ status,
+                     const int32_t* __restrict__ slot_of, const int32_t* __restrict__ order,
+                     const float* __restrict__ lse2, float* __restrict__ delta, float* __restrict__ d_qkv, int* __restrict__ counter, int* __restrict__ status,
                      int N, int F, float out_scale0, float out_scale1, int out_ld, int out_c0, int out_c1,
                      long long* __restrict__ prof) {
   using Smem = BwdSmem<MODE>;
@@ -97,15 +98,15 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sm.own_full[i], 1);
-      mbar_init(&sm.own_empty[i], 1 + kEwWarps + 2);
+      mbar_init(&sm.own_empty[i], 1 + kEwWarps + kTWarps);
       mbar_init(&sm.xy_full[i], 1);
       mbar_init(&sm.xy_empty[i], kEwWarps);
       mbar_init(&sm.u_full[i], kEwWarps);
-      mbar_init(&sm.t_full[i], 2);
+      mbar_init(&sm.t_full[i], kTWarps);
     }
     for (int i = 0; i < NS; ++i) {
       mbar_init(&sm.edge_full[i], 1);
-      mbar_init(&sm.edge_empty[i], MODE == MODE_DKV ? 3 + kEwWarps : 3);
+      mbar_init(&sm.edge_empty[i], MODE == MODE_DKV ? 1 + kTWarps + kEwWarps : 1 + kTWarps);
     }
     fence_barrier_init();
   }
@@ -130,7 +131,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       int node = -1, eb = 0, ee = 0;
       if (lane == 0) {
         const int idx = atomicAdd(counter, 1);
-        node = idx < N ? idx : -1;
+        node = idx < N ? (order ? order[idx] : idx) : -1;
         if (node >= 0) {
           eb = rowptr[node];
           ee = rowptr[node + 1];
@@ -235,7 +236,9 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
     // ------------------------------------------------------------------ T MMAs: one warp issues TX = X' * B_tx, the other TY = Y' * B_ty
     //   (A = the bf16 operand the elementwise warps wrote back into TMEM, B = an edge tile as MN-major operand)
     {
-      const uint32_t which = warp - (kEwWarps + 2);            // 0: TX, 1: TY
+      const uint32_t tw = warp - (kEwWarps + 2);
+      const uint32_t which = tw >> 1;                          // 0: TX, 1: TY
+      const int ks0 = 4 * (tw & 1);                            // this warp's K steps: [ks0, ks0 + 4)
       const uint32_t idesc_t = idesc_bf16(128, 16, 0, 1);      // N = 16 per MMA (two per K step when hd = 32)
       const int btile = (which == 0 && MODE == MODE_DKV) ? 1 : 0;   // TX of the dK/dV pass multiplies dO; all others tile 0
       uint32_t qi = 0, edge = 0, c = 0;
@@ -255,14 +258,18 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
             tc_fence_after();
             const uint32_t a_col = tmem + set * 256 + which * 128;
             const uint64_t bd = smem_desc(smem_u32(sm.edge[st][btile]) + h * (HD * 2), 16, 1024, LAYOUT_SW128);
+            // every T MMA accumulates: the elementwise warps zeroed the T tiles, so the K steps of one tile may be
+            // issued by two warps in any order
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks)
+            for (int kk = 0; kk < 4; ++kk) {
+              const int ks = ks0 + kk;
               if (ks < ksteps) {
                 const uint32_t a_addr = a_col + 32 * (ks >> 1) + 8 * (ks & 1);
 #pragma unroll
                 for (int half = 0; half < HD / 16; ++half)
-                  mma_ts_w(a_col + 16 + 32 * half, a_addr, desc_advance(bd, ks * 2048 + half * 32), idesc_t, ks > 0);
+                  mma_ts_w(a_col + 16 + 32 * half, a_addr, desc_advance(bd, ks * 2048 + half * 32), idesc_t, 1u);
               }
+            }
             mma_commit_w(&sm.t_full[set]);
           }
           mma_commit_w(&sm.edge_empty[st]);
@@ -394,6 +401,12 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
               if (!readback(c - 1, (h + H - 1) % H, e_prev)) AMP_FAIL(304);
             }
           }
+          // zero the T tiles of this set (they live in the second half of this group's own, already consumed, score columns)
+          if (g < HD / 16) {
+            const uint32_t z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+            tmem_st_32x32b_x16(xbase + 16, z);
+            tmem_st_32x32b_x16(xbase + 128 + 16, z);
+          }
           if (MODE == MODE_DQ) sm.dl[set][g][row] = dl0 + dl1;
           AMP_PHASE(1);
           tmem_st_wait();
@@ -451,19 +464,19 @@ long long* g_bwd_prof = nullptr;   // debug: set through ampconv_debug_set_bwd_p
 
 template <int HD, int MODE>
 int launch_bwd(const CUtensorMap& own0, const CUtensorMap& own1, const CUtensorMap& oth0, const CUtensorMap& oth1,
-               const int32_t* rowptr, const int32_t* nbr, const int32_t* slot_of, const float* lse2, float* delta,
-               float* d_qkv, int* counter, int* status, int N, int F, float s0, float s1, int out_ld, int out_c0,
+               const int32_t* rowptr, const int32_t* nbr, const int32_t* slot_of, const int32_t* order, const float* lse2,
+               float* delta, float* d_qkv, int* counter, int* status, int N, int F, float s0, float s1, int out_ld, int out_c0,
                int out_c1, cudaStream_t stream) {
   const size_t smem = sizeof(BwdSmem<MODE>) + 1024;
   const int grid = N < sm_count() ? N : sm_count();
   long long* prof = g_bwd_prof;
   if (prof) {
     AMPCONV_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_bf16_kernel<HD, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_bwd_bf16_kernel<HD, MODE, true><<<grid, kThreads, smem, stream>>>(own0, own1, oth0, oth1, rowptr, nbr, slot_of, lse2, delta,
+    attn_bwd_bf16_kernel<HD, MODE, true><<<grid, kThreads, smem, stream>>>(own0, own1, oth0, oth1, rowptr, nbr, slot_of, order, lse2, delta,
                                                                           d_qkv, counter, status, N, F, s0, s1, out_ld, out_c0, out_c1, prof);
   } else {
     AMPCONV_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_bf16_kernel<HD, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_bwd_bf16_kernel<HD, MODE, false><<<grid, kThreads, smem, stream>>>(own0, own1, oth0, oth1, rowptr, nbr, slot_of, lse2, delta,
+    attn_bwd_bf16_kernel<HD, MODE, false><<<grid, kThreads, smem, stream>>>(own0, own1, oth0, oth1, rowptr, nbr, slot_of, order, lse2, delta,
                                                                            d_qkv, counter, status, N, F, s0, s1, out_ld, out_c0, out_c1, nullptr);
   }
   AMPCONV_CHECK_LAUNCH();
@@ -479,8 +492,8 @@ extern "C" int ampconv_attn_bf16_supported(int F, int d, int H);
 
 // N_own: nodes the pass iterates over (destinations for MODE_DQ, sources for MODE_DKV); N_oth: nodes of the edge tiles.
 static int bwd_common(int mode, const void* q, const void* k, const void* v, const void* d_agg_bf16,
-                      const int32_t* rowptr, const int32_t* nbr, const int32_t* slot_of, const float* lse2, float* delta,
-                      float* out, int out_ld, int out_c0, int out_c1, int64_t N_dst, int64_t N_kv, int64_t E, int F, int d,
+                      const int32_t* rowptr, const int32_t* nbr, const int32_t* slot_of, const int32_t* order,
+                      const float* lse2, float* delta, float* out, int out_ld, int out_c0, int out_c1, int64_t N_dst, int64_t N_kv, int64_t E, int F, int d,
                       int H, void* workspace, size_t workspace_bytes, void* stream_) {
   AMPCONV_REQUIRE(N_dst >= 0 && N_kv >= 0 && E >= 0 && F > 0 && d > 0 && H > 0 && d % H == 0);
   if (!ampconv_attn_bf16_supported(F, d, H)) return AMPCONV_ERR_UNSUPPORTED;
@@ -504,33 +517,33 @@ static int bwd_common(int mode, const void* q, const void* k, const void* v, con
   if (mode == MODE_DQ) {
     // dQ = hd^-1/2 * (dS K)
     if (hd == 16)
-      return launch_bwd<16, MODE_DQ>(mq, mg, mk, mv, rowptr, nbr, slot_of, lse2, delta, out, counter, status, (int)N_own, F,
+      return launch_bwd<16, MODE_DQ>(mq, mg, mk, mv, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)N_own, F,
                                     inv_sqrt_hd, 0.f, out_ld, out_c0, out_c1, stream);
-    return launch_bwd<32, MODE_DQ>(mq, mg, mk, mv, rowptr, nbr, slot_of, lse2, delta, out, counter, status, (int)N_own, F,
+    return launch_bwd<32, MODE_DQ>(mq, mg, mk, mv, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)N_own, F,
                                   inv_sqrt_hd, 0.f, out_ld, out_c0, out_c1, stream);
   }
   // dK = hd^-1/2 * dS^T Q = ln2 * dS^T Q'  (Q' = Q * log2e / sqrt(hd)),  dV = P^T dO
   if (hd == 16)
-    return launch_bwd<16, MODE_DKV>(mk, mv, mq, mg, rowptr, nbr, slot_of, lse2, delta, out, counter, status, (int)N_own, F,
+    return launch_bwd<16, MODE_DKV>(mk, mv, mq, mg, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)N_own, F,
                                    ln2, 1.f, out_ld, out_c0, out_c1, stream);
-  return launch_bwd<32, MODE_DKV>(mk, mv, mq, mg, rowptr, nbr, slot_of, lse2, delta, out, counter, status, (int)N_own, F, ln2,
+  return launch_bwd<32, MODE_DKV>(mk, mv, mq, mg, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)N_own, F, ln2,
                                  1.f, out_ld, out_c0, out_c1, stream);
 }
 
 extern "C" int ampconv_attn_bwd_dq_bf16(const void* q, const void* k, const void* v, const void* d_agg_bf16,
                                         const float* lse2, const int32_t* dst_rowptr, const int32_t* dst_src,
-                                        float* d_qkv, float* delta, int64_t N, int64_t E, int F, int d, int H,
-                                        void* workspace, size_t workspace_bytes, void* stream) {
-  return bwd_common(MODE_DQ, q, k, v, d_agg_bf16, dst_rowptr, dst_src, nullptr, lse2, delta, d_qkv, 3 * kD, 0, 0, N, N, E, F,
+                                        const int32_t* order, float* d_qkv, float* delta, int64_t N, int64_t E, int F,
+                                        int d, int H, void* workspace, size_t workspace_bytes, void* stream) {
+  return bwd_common(MODE_DQ, q, k, v, d_agg_bf16, dst_rowptr, dst_src, nullptr, order, lse2, delta, d_qkv, 3 * kD, 0, 0, N, N, E, F,
                     d, H, workspace, workspace_bytes, stream);
 }
 
 extern "C" int ampconv_attn_bwd_dkv_bf16(const void* q, const void* k, const void* v, const void* d_agg_bf16,
                                          const float* lse2, const float* delta, const int32_t* src_rowptr,
-                                         const int32_t* src_dst, const int32_t* src_pos, float* d_qkv,
-                                         int64_t N, int64_t E, int F, int d, int H,
+                                         const int32_t* src_dst, const int32_t* src_pos, const int32_t* order,
+                                         float* d_qkv, int64_t N, int64_t E, int F, int d, int H,
                                          void* workspace, size_t workspace_bytes, void* stream) {
-  return bwd_common(MODE_DKV, q, k, v, d_agg_bf16, src_rowptr, src_dst, src_pos, lse2, const_cast<float*>(delta), d_qkv,
+  return bwd_common(MODE_DKV, q, k, v, d_agg_bf16, src_rowptr, src_dst, src_pos, order, lse2, const_cast<float*>(delta), d_qkv,
                     3 * kD, kD, 2 * kD, N, N, E, F, d, H, workspace, workspace_bytes, stream);
 }
 
@@ -539,18 +552,19 @@ extern "C" int ampconv_attn_bwd_dkv_bf16(const void* q, const void* k, const voi
 // d_k | d_v fp32 [num_kv_nodes*F, 128] of the local edges (to be reduce-scattered to the owners).
 extern "C" int ampconv_attn_bwd_dq_bf16_part(const void* q, const void* k, const void* v, const void* d_agg_bf16,
                                              const float* lse2, const int32_t* dst_rowptr, const int32_t* dst_src,
-                                             float* d_q, float* delta, int64_t num_nodes, int64_t num_kv_nodes, int64_t E,
-                                             int F, int d, int H, void* workspace, size_t workspace_bytes, void* stream) {
-  return bwd_common(MODE_DQ, q, k, v, d_agg_bf16, dst_rowptr, dst_src, nullptr, lse2, delta, d_q, kD, 0, 0, num_nodes,
+                                             const int32_t* order, float* d_q, float* delta, int64_t num_nodes,
+                                             int64_t num_kv_nodes, int64_t E, int F, int d, int H, void* workspace,
+                                             size_t workspace_bytes, void* stream) {
+  return bwd_common(MODE_DQ, q, k, v, d_agg_bf16, dst_rowptr, dst_src, nullptr, order, lse2, delta, d_q, kD, 0, 0, num_nodes,
                     num_kv_nodes, E, F, d, H, workspace, workspace_bytes, stream);
 }
 
 extern "C" int ampconv_attn_bwd_dkv_bf16_part(const void* q, const void* k, const void* v, const void* d_agg_bf16,
                                               const float* lse2, const float* delta, const int32_t* src_rowptr,
-                                              const int32_t* src_dst, const int32_t* src_pos, float* d_kv,
-                                              int64_t num_nodes, int64_t num_kv_nodes, int64_t E, int F, int d, int H,
-                                              void* workspace, size_t workspace_bytes, void* stream) {
-  return bwd_common(MODE_DKV, q, k, v, d_agg_bf16, src_rowptr, src_dst, src_pos, lse2, const_cast<float*>(delta), d_kv,
+                                              const int32_t* src_dst, const int32_t* src_pos, const int32_t* order,
+                                              float* d_kv, int64_t num_nodes, int64_t num_kv_nodes, int64_t E, int F, int d,
+                                              int H, void* workspace, size_t workspace_bytes, void* stream) {
+  return bwd_common(MODE_DKV, q, k, v, d_agg_bf16, src_rowptr, src_dst, src_pos, order, lse2, const_cast<float*>(delta), d_kv,
                     2 * kD, 0, kD, num_nodes, num_kv_nodes, E, F, d, H, workspace, workspace_bytes, stream);
 }
 

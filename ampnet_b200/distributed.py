@@ -97,6 +97,8 @@ class BipartiteGraph:
                       _lib.i64(num_src), self.dst_rowptr, self.dst_src, self.dst_eid, self.src_rowptr, self.src_dst,
                       self.src_pos, self.inv_deg, self.has_in, ws, _lib.size_t(ws.numel()),
                       _lib.stream_ptr(torch.cuda.current_stream(dev)))
+        self.order_dst = torch.argsort(self.dst_rowptr[1:] - self.dst_rowptr[:-1], descending=True).to(torch.int32)
+        self.order_src = torch.argsort(self.src_rowptr[1:] - self.src_rowptr[:-1], descending=True).to(torch.int32)
 
 
 # ------------------------------------------------------------------------------------------ collectives (NCCL or gloo)
@@ -147,7 +149,7 @@ class _DistAMPConvFunction(torch.autograd.Function):
             agg = torch.empty((rows, d), dtype=torch.float32, device=dev)
             lse2 = torch.empty((g.num_edges, num_heads, (f + 3) // 4 * 4), dtype=torch.float32, device=dev)
             out = torch.empty((n, width), dtype=torch.float32, device=dev)
-            _lib.call("ampconv_attn_fwd_bf16_part", q, k_all, v_all, g.dst_rowptr, g.dst_src, g.inv_deg, agg, lse2,
+            _lib.call("ampconv_attn_fwd_bf16_part", q, k_all, v_all, g.dst_rowptr, g.dst_src, g.inv_deg, g.order_dst, agg, lse2,
                       _lib.i64(n), _lib.i64(pg.num_kv_nodes), _lib.i64(g.num_edges), _lib.i32(f), _lib.i32(d),
                       _lib.i32(num_heads), ws, _lib.size_t(256), st)
             _lib.call("ampconv_out_proj_tc", agg, w_out, b_out, g.has_in, out, _lib.i64(n), _lib.i32(f), _lib.i32(d), ws, st)
@@ -181,10 +183,11 @@ class _DistAMPConvFunction(torch.autograd.Function):
             delta = torch.empty_like(lse2)
             tail = (_lib.i64(n), _lib.i64(pg.num_kv_nodes), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(h), bws,
                     _lib.size_t(256), st)
-            _lib.call("ampconv_attn_bwd_dq_bf16_part", q, k_all, v_all, d_agg, lse2, g.dst_rowptr, g.dst_src, d_q, delta, *tail)
+            _lib.call("ampconv_attn_bwd_dq_bf16_part", q, k_all, v_all, d_agg, lse2, g.dst_rowptr, g.dst_src, g.order_dst, d_q, delta,
+                      *tail)
             d_kv_partial = torch.empty((pg.num_kv_nodes * f, 2 * d), dtype=torch.float32, device=dev)
             _lib.call("ampconv_attn_bwd_dkv_bf16_part", q, k_all, v_all, d_agg, lse2, delta, g.src_rowptr, g.src_dst,
-                      g.src_pos, d_kv_partial, *tail)
+                      g.src_pos, g.order_src, d_kv_partial, *tail)
             d_kv = reduce_scatter_rows(d_kv_partial, pg.world, pg.rank, group)        # [max_n * F, 2d], rows >= n*F are padding
             del d_kv_partial
             d_qkv = torch.cat([d_q, d_kv[:rows]], dim=1)

@@ -103,7 +103,7 @@ def _forward_bf16(x, graph, w_in, b_in, w_out, b_out, num_heads):
     ws = torch.zeros(64, dtype=torch.int32, device=dev)
     _lib.call("ampconv_qkv_proj_tc", x, w_in, b_in, q, k, v, _lib.i64(rows), _lib.i32(d),
               _lib.f32(LOG2E / hd ** 0.5), ws, st)
-    _lib.call("ampconv_attn_fwd_bf16", q, k, v, graph.dst_rowptr, graph.dst_src, graph.inv_deg, None, agg, lse2,
+    _lib.call("ampconv_attn_fwd_bf16", q, k, v, graph.dst_rowptr, graph.dst_src, graph.inv_deg, graph.order_dst, agg, lse2,
               _lib.i64(n), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(num_heads),
               ws, _lib.size_t(ws.numel() * 4), st)
     _lib.call("ampconv_out_proj_tc", agg, w_out, b_out, graph.has_in, out,
@@ -162,9 +162,9 @@ def _backward_bf16(saved, x, w_in, w_out, d_out):
     d_qkv = torch.empty((rows, 3 * d), dtype=torch.float32, device=dev)
     delta = torch.empty_like(lse2)
     tail = (_lib.i64(n), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(h), bws, _lib.size_t(bws.numel() * 4), st)
-    _lib.call("ampconv_attn_bwd_dq_bf16", q, k, v, d_agg, lse2, g.dst_rowptr, g.dst_src, d_qkv, delta, *tail)
+    _lib.call("ampconv_attn_bwd_dq_bf16", q, k, v, d_agg, lse2, g.dst_rowptr, g.dst_src, g.order_dst, d_qkv, delta, *tail)
     _lib.call("ampconv_attn_bwd_dkv_bf16", q, k, v, d_agg, lse2, delta, g.src_rowptr, g.src_dst, g.src_pos,
-              d_qkv, *tail)
+              g.order_src, d_qkv, *tail)
     d_x = torch.empty_like(x)
     d_w_in = torch.empty_like(w_in)
     d_b_in = torch.empty(3 * d, dtype=torch.float32, device=dev)
@@ -274,7 +274,7 @@ def profile_stages(x, graph, w_in, b_in, w_out, b_out, num_heads, d_out, mode, r
         if mode == "bf16":
             q, k, v, lse2, bws = saved.bf16
             calls["attn_fwd"] = lambda: _lib.call(
-                "ampconv_attn_fwd_bf16", q, k, v, graph.dst_rowptr, graph.dst_src, graph.inv_deg, None, saved.agg, lse2,
+                "ampconv_attn_fwd_bf16", q, k, v, graph.dst_rowptr, graph.dst_src, graph.inv_deg, graph.order_dst, saved.agg, lse2,
                 _lib.i64(n), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(num_heads), bws,
                 _lib.size_t(bws.numel() * 4), st)
         else:
@@ -287,9 +287,9 @@ def profile_stages(x, graph, w_in, b_in, w_out, b_out, num_heads, d_out, mode, r
             tail = (_lib.i64(n), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(num_heads), bws,
                     _lib.size_t(bws.numel() * 4), st)
             calls["attn_bwd_dq"] = lambda: _lib.call("ampconv_attn_bwd_dq_bf16", q, k, v, d_agg16, lse2,
-                                                     graph.dst_rowptr, graph.dst_src, d_qkv, delta2, *tail)
+                                                     graph.dst_rowptr, graph.dst_src, graph.order_dst, d_qkv, delta2, *tail)
             calls["attn_bwd_dkv"] = lambda: _lib.call("ampconv_attn_bwd_dkv_bf16", q, k, v, d_agg16, lse2, delta2,
-                                                      graph.src_rowptr, graph.src_dst, graph.src_pos, d_qkv, *tail)
+                                                      graph.src_rowptr, graph.src_dst, graph.src_pos, graph.order_src, d_qkv, *tail)
         else:
             delta = torch.empty_like(saved.lse)
             calls["attn_bwd_dq"] = lambda: _lib.call("ampconv_attn_bwd_dq_f32", saved.qkv, d_agg, saved.lse,

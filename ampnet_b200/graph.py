@@ -42,7 +42,9 @@ class Graph:
                       self.src_rowptr, self.src_dst, self.src_pos,
                       self.inv_deg, self.has_in, ws, _lib.size_t(ws.numel()),
                       _lib.stream_ptr(torch.cuda.current_stream(dev)))
-        self._extras = {}
+        # longest-processing-time-first node orders for the persistent tcgen05 kernels (dynamic scheduler)
+        self.order_dst = torch.argsort(self.dst_rowptr[1:] - self.dst_rowptr[:-1], descending=True).to(torch.int32)
+        self.order_src = torch.argsort(self.src_rowptr[1:] - self.src_rowptr[:-1], descending=True).to(torch.int32)
 
 
 _cache = {}

@@ -206,14 +206,15 @@ AMPCONV_API int ampconv_out_proj_bwd_bf16(const float* d_out, const float* agg, 
  *   _dq : destination-sorted; writes d_qkv[:, 0:d] (fp32 [rows,3d]) and delta[p,h,i];
  *   _dkv: source-sorted; reads delta; writes d_qkv[:, d:3d].
  * lse2 / delta use a row stride of roundup4(F): shape [E, H, roundup4(F)].
+ * order: optional processing order of the pass's nodes (longest edge list first balances the persistent CTAs); NULL = 0..N-1.
  * Same workspace as the forward call (>= 256 bytes). */
 AMPCONV_API int ampconv_attn_bwd_dq_bf16(const void* q, const void* k, const void* v, const void* d_agg_bf16,
                              const float* lse2, const int32_t* dst_rowptr, const int32_t* dst_src,
-                             float* d_qkv, float* delta, int64_t num_nodes, int64_t num_edges, int F, int d, int H,
+                             const int32_t* order, float* d_qkv, float* delta, int64_t num_nodes, int64_t num_edges, int F, int d, int H,
                              void* workspace, size_t workspace_bytes, void* stream);
 AMPCONV_API int ampconv_attn_bwd_dkv_bf16(const void* q, const void* k, const void* v, const void* d_agg_bf16,
                               const float* lse2, const float* delta, const int32_t* src_rowptr,
-                              const int32_t* src_dst, const int32_t* src_pos, float* d_qkv,
+                              const int32_t* src_dst, const int32_t* src_pos, const int32_t* order, float* d_qkv,
                               int64_t num_nodes, int64_t num_edges, int F, int d, int H,
                               void* workspace, size_t workspace_bytes, void* stream);
 
@@ -252,15 +253,17 @@ AMPCONV_API int ampconv_qkv_proj_bwd_params_tc(const float* x, const float* d_qk
  * fp32 [num_kv_nodes*F, 2d] contributed by the local edges (the host reduce-scatters it to the owners). */
 AMPCONV_API int ampconv_attn_fwd_bf16_part(const void* q, const void* k, const void* v,
                                const int32_t* dst_rowptr, const int32_t* dst_src, const float* inv_deg,
-                               float* agg, float* lse2, int64_t num_nodes, int64_t num_kv_nodes, int64_t num_edges,
+                               const int32_t* order, float* agg, float* lse2, int64_t num_nodes, int64_t num_kv_nodes,
+                               int64_t num_edges,
                                int F, int d, int H, void* workspace, size_t workspace_bytes, void* stream);
 AMPCONV_API int ampconv_attn_bwd_dq_bf16_part(const void* q, const void* k, const void* v, const void* d_agg_bf16,
                                   const float* lse2, const int32_t* dst_rowptr, const int32_t* dst_src,
-                                  float* d_q, float* delta, int64_t num_nodes, int64_t num_kv_nodes, int64_t num_edges,
+                                  const int32_t* order, float* d_q, float* delta, int64_t num_nodes, int64_t num_kv_nodes,
+                                  int64_t num_edges,
                                   int F, int d, int H, void* workspace, size_t workspace_bytes, void* stream);
 AMPCONV_API int ampconv_attn_bwd_dkv_bf16_part(const void* q, const void* k, const void* v, const void* d_agg_bf16,
                                    const float* lse2, const float* delta, const int32_t* src_rowptr,
-                                   const int32_t* src_dst, const int32_t* src_pos, float* d_kv,
+                                   const int32_t* src_dst, const int32_t* src_pos, const int32_t* order, float* d_kv,
                                    int64_t num_nodes, int64_t num_kv_nodes, int64_t num_edges, int F, int d, int H,
                                    void* workspace, size_t workspace_bytes, void* stream);
 

@@ -61,9 +61,9 @@ def bwd():
         prof.zero_()
         lib.ampconv_debug_set_bwd_profile(ctypes.c_void_p(prof.data_ptr()))
         if mode == "dq":
-            _lib.call("ampconv_attn_bwd_dq_bf16", q, k, v, do, lse2, g.dst_rowptr, g.dst_src, dqkv, delta, *tail)
+            _lib.call("ampconv_attn_bwd_dq_bf16", q, k, v, do, lse2, g.dst_rowptr, g.dst_src, None, dqkv, delta, *tail)
         else:
-            _lib.call("ampconv_attn_bwd_dkv_bf16", q, k, v, do, lse2, delta, g.src_rowptr, g.src_dst, g.src_pos, dqkv, *tail)
+            _lib.call("ampconv_attn_bwd_dkv_bf16", q, k, v, do, lse2, delta, g.src_rowptr, g.src_dst, g.src_pos, None, dqkv, *tail)
         torch.cuda.synchronize()
         lib.ampconv_debug_set_bwd_profile(ctypes.c_void_p(0))
         p = prof.cpu().tolist()
