@@ -201,18 +201,25 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
     {
       const uint32_t idesc_xy = idesc_bf16(128, nqk, 0, 0);
       uint32_t qi = 0, edge = 0, c = 0;
+      const bool do_prof = PROF && blockIdx.x == 0;
+      long long pm[4] = {0, 0, 0, 0};
+      long long tp = do_prof ? clock64() : 0;
+#define AMP_MPHASE(i) do { if (do_prof) { const long long now_ = clock64(); pm[i] += now_ - tp; tp = now_; } } while (0)
       for (;; ++qi) {
         const uint32_t qb = qi & 1;
         AMP_WAIT(&sm.own_full[qb], (qi >> 1) & 1, 201);
         const NodeSlot ns = sm.slot[qb];
         if (ns.node < 0) break;
+        AMP_MPHASE(3);
         for (int e = ns.e_begin; e < ns.e_end; ++e, ++edge) {
           const uint32_t st = edge % NS;
           AMP_WAIT(&sm.edge_full[st], (edge / NS) & 1, 202);
+          AMP_MPHASE(0);
 #pragma unroll
           for (int h = 0; h < H; ++h, ++c) {
             const uint32_t set = c & 1;
             AMP_WAIT(&sm.xy_empty[set], ((c >> 1) & 1) ^ 1, 203);
+            AMP_MPHASE(1);
             tc_fence_after();
             const uint32_t hb = h * (HD * 2);
             const uint64_t a0 = smem_desc(smem_u32(sm.own[qb][0]) + hb, 16, 1024, LAYOUT_SW128);
@@ -226,11 +233,17 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
             for (int ks = 0; ks < HD / 16; ++ks)
               mma_ss_w(tmem + set * 256 + 128, desc_advance(a1, ks * 32), desc_advance(b1, ks * 32), idesc_xy, ks > 0);
             mma_commit_w(&sm.xy_full[set]);
+            AMP_MPHASE(2);
           }
           mma_commit_w(&sm.edge_empty[st]);
           if (e + 1 == ns.e_end) mma_commit_w(&sm.own_empty[qb]);
         }
       }
+      if (do_prof && lane == 0) {
+        for (int i = 0; i < 4; ++i) prof[32 + i] = pm[i];
+        prof[36] = c;
+      }
+#undef AMP_MPHASE
     }
   } else if (warp >= kEwWarps + 2) {
     // ------------------------------------------------------------------ T MMAs: one warp issues TX = X' * B_tx, the other TY = Y' * B_ty
@@ -242,6 +255,10 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       const uint32_t idesc_t = idesc_bf16(128, 16, 0, 1);      // N = 16 per MMA (two per K step when hd = 32)
       const int btile = (which == 0 && MODE == MODE_DKV) ? 1 : 0;   // TX of the dK/dV pass multiplies dO; all others tile 0
       uint32_t qi = 0, edge = 0, c = 0;
+      const bool do_prof = PROF && blockIdx.x == 0 && tw == 0;
+      long long pm[4] = {0, 0, 0, 0};
+      long long tp = do_prof ? clock64() : 0;
+#define AMP_TPHASE(i) do { if (do_prof) { const long long now_ = clock64(); pm[i] += now_ - tp; tp = now_; } } while (0)
       for (;; ++qi) {
         const uint32_t qb = qi & 1;
         AMP_WAIT(&sm.own_full[qb], (qi >> 1) & 1, 211);
@@ -254,7 +271,9 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
 #pragma unroll
           for (int h = 0; h < H; ++h, ++c) {
             const uint32_t set = c & 1;
+            AMP_TPHASE(3);
             AMP_WAIT(&sm.u_full[set], (c >> 1) & 1, 213);
+            AMP_TPHASE(0);
             tc_fence_after();
             const uint32_t a_col = tmem + set * 256 + which * 128;
             const uint64_t bd = smem_desc(smem_u32(sm.edge[st][btile]) + h * (HD * 2), 16, 1024, LAYOUT_SW128);
@@ -271,10 +290,20 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
               }
             }
             mma_commit_w(&sm.t_full[set]);
+            AMP_TPHASE(1);
+            if (do_prof) {
+              AMP_WAIT(&sm.t_full[set], (c >> 1) & 1, 214);   // observe only: how long until all four T warps' MMAs have landed
+              AMP_TPHASE(2);
+            }
           }
           mma_commit_w(&sm.edge_empty[st]);
         }
       }
+      if (do_prof && lane == 0) {
+        for (int i = 0; i < 4; ++i) prof[40 + i] = pm[i];
+        prof[44] = c;
+      }
+#undef AMP_TPHASE
     }
   } else {
     // ------------------------------------------------------------------ elementwise warps
@@ -285,7 +314,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
     constexpr int HQ = HD / 4;                      // T columns this thread reads back per head
     uint32_t qi = 0, c = 0, ei = 0;
     float* acc = &sm.acc[0][threadIdx.x];           // element x of this thread: acc[x * 512]
-    const bool do_prof = PROF && blockIdx.x == 0;
+    const bool do_prof = PROF && blockIdx.x == 0 && (warp == 0 || warp == kEwWarps - 1);
     long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tp = do_prof ? clock64() : 0;
 #define AMP_PHASE(i) do { if (do_prof) { const long long now_ = clock64(); pt[i] += now_ - tp; tp = now_; } } while (0)
@@ -448,9 +477,10 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       AMP_PHASE(7);
       ++qi;
     }
-    if (do_prof && threadIdx.x == 0) {
-      for (int i = 0; i < 8; ++i) prof[i] = pt[i];
-      prof[8] = c;
+    if (do_prof && lane == 0) {
+      long long* pr = prof + (warp == 0 ? 0 : 16);
+      for (int i = 0; i < 8; ++i) pr[i] = pt[i];
+      pr[8] = c;
     }
 #undef AMP_PHASE
   }
@@ -568,7 +598,7 @@ extern "C" int ampconv_attn_bwd_dkv_bf16_part(const void* q, const void* k, cons
                     2 * kD, 0, kD, num_nodes, num_kv_nodes, E, F, d, H, workspace, workspace_bytes, stream);
 }
 
-// Debug: when set to a device buffer of 9 int64, the next backward launches run the instrumented kernel and fill it
+// Debug: when set to a device buffer of 64 int64, the next backward launches run the instrumented kernel and fill it
 // with the cycles one elementwise warp spent per phase (wait X/Y, chunks, publish, wait T, fold T, stats load,
 // node wait, node epilogue) and its item count.  NULL restores the product kernels.
 extern "C" int ampconv_debug_set_bwd_profile(long long* prof) {

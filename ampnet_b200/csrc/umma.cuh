@@ -282,6 +282,18 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// volatile variant: keeps its program order relative to other volatile asm (hand software pipelining)
+__device__ __forceinline__ float ex2_approx_v(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 3-input max (FMNMX3 on sm_100)
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
 __device__ __forceinline__ uint32_t ex2_bf16x2(uint32_t x) {
   uint32_t y;
   asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(x));

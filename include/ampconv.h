@@ -191,7 +191,7 @@ AMPCONV_API int ampconv_attn_fwd_bf16_profile(const void* q, const void* k, cons
                                   int64_t num_nodes, int64_t num_edges, int F, int d, int H,
                                   void* workspace, size_t workspace_bytes, void* stream, long long* prof);
 
-/* Debug: device buffer of 9 int64 (or NULL) that makes the tcgen05 backward kernels record per-phase cycles. */
+/* Debug: device buffer of 64 int64 (or NULL) that makes the tcgen05 backward kernels record per-phase cycles. */
 AMPCONV_API int ampconv_debug_set_bwd_profile(long long* prof);
 
 /* Backward of ampconv_out_proj_f32 for the bf16 family: identical, except that d_agg (already

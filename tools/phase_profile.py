@@ -25,7 +25,7 @@ def main():
                   _lib.i64(n), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(h), ws, _lib.size_t(256), st, prof)
     torch.cuda.synchronize()
     p = prof.cpu().tolist()
-    names = ["wait S", "load S", "max", "wait P slot", "exp+pack+scale", "st P + publish + lse", "wait O (node end)", "-",
+    names = ["wait S", "load S", "max", "wait P slot", "exp+pack+scale", "st P + publish + lse", "wait O (node end)", "wait MUFU token",
              "node wait", "node epilogue"]
     items = max(1, p[10])
     tot = sum(p[:10])
@@ -54,7 +54,7 @@ def bwd():
     st = _lib.stream_ptr(torch.cuda.current_stream(dev))
     tail = (_lib.i64(n), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(h), ws, _lib.size_t(256), st)
     _lib.call("ampconv_attn_fwd_bf16", q, k, v, g.dst_rowptr, g.dst_src, g.inv_deg, None, agg, lse2, *tail)
-    prof = torch.zeros(16, dtype=torch.int64, device=dev)
+    prof = torch.zeros(64, dtype=torch.int64, device=dev)
     lib = _lib.load()
     names = ["wait X/Y", "chunks (ld, exp, pack, st)", "publish", "wait T", "fold T", "stats/lse load", "node wait", "node epilogue"]
     for mode in ("dq", "dkv"):
@@ -72,6 +72,17 @@ def bwd():
         print(f"bwd {mode}: items={items} total cycles/item={tot / items:.0f}")
         for nm, cyc in zip(names, p[:8]):
             print(f"  {nm:28s} {cyc / items:8.1f} cyc/item  {100.0 * cyc / tot:5.1f}%")
+        if p[24] > 0:
+            it2 = p[24]
+            print("  last elementwise warp: " + ", ".join(f"{nm} {cyc / it2:.0f}" for nm, cyc in zip(names, p[16:24])))
+        if p[36] > 0:
+            it3 = p[36]
+            print(f"  score-MMA warp /item: wait edge tiles {p[32] / it3:.0f}, wait set free {p[33] / it3:.0f}, "
+                  f"issue+commit {p[34] / it3:.0f}, node wait {p[35] / it3:.0f}")
+        if p[44] > 0:
+            it4 = p[44]
+            print(f"  T-MMA warp 0 /item: wait operands {p[40] / it4:.0f}, issue+commit {p[41] / it4:.0f}, "
+                  f"until T complete {p[42] / it4:.0f}, other {p[43] / it4:.0f}")
 
 
 if __name__ == "__main__":
