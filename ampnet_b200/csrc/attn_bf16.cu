@@ -22,7 +22,6 @@
 // Layouts: Q', K, V are bf16 [N, F, 64] node-major, rows of 128 bytes; Q' is pre-multiplied by
 // log2(e)/sqrt(hd) so that scores are in the log2 domain.  lse2[p,h,i] = max + log2(sum) per
 // destination-sorted edge slot p is saved for the backward recompute.
-#include <cstdlib>
 #include <cuda_bf16.h>
 #include <math_constants.h>
 
@@ -52,7 +51,6 @@ struct FwdSmem {
   uint64_t kv_full[kStages], kv_empty[kStages];
   uint64_t s_full[2], s_empty[2], p_full[2], p_empty[2];
   uint64_t o_full[2], o_empty[2];     // per node parity: O tile complete / read back
-  uint64_t tok[2][4];                 // MUFU token of SM sub-partition q: tok[b][q] = "warp q of warpgroup b may run its exp phase"
   NodeSlot slot[2];
   uint32_t tmem_base;
 };
@@ -74,8 +72,7 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
                      const __grid_constant__ CUtensorMap mapV, const int32_t* __restrict__ rowptr,
                      const int32_t* __restrict__ dst_src, const float* __restrict__ inv_deg,
                      const int32_t* __restrict__ order, int* __restrict__ counter, int* __restrict__ status,
-                     float* __restrict__ agg, float* __restrict__ lse2, int N, int F, int use_token,
-                     long long* __restrict__ prof) {
+                     float* __restrict__ agg, float* __restrict__ lse2, int N, int F, long long* __restrict__ prof) {
   constexpr int H = kD / HD;        // heads
   constexpr int HL = H / 2;         // heads per softmax warpgroup (head h belongs to warpgroup h & 1)
   static_assert(H % 2 == 0, "this kernel splits heads between two warpgroups");
@@ -99,9 +96,7 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       mbar_init(&sm.kv_full[i], 1);
       mbar_init(&sm.kv_empty[i], 3);
     }
-    for (int i = 0; i < 8; ++i) mbar_init(&sm.tok[i >> 2][i & 3], 1);
     fence_barrier_init();
-    for (int i = 0; i < 4; ++i) mbar_arrive(&sm.tok[0][i]);   // warpgroup 0 goes first
   }
   if (warp == 8 && lane == 0) {
     prefetch_tensormap(&mapQ);
@@ -287,43 +282,27 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
             for (int j = 0; j < 128; ++j)
               if (j >= F) s[j] = __float_as_uint(-CUDART_INF_F);
           }
-          // row max: 8 independent chains of 3-input max (FMNMX3)
           float mx[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) mx[u] = fmaxf(__uint_as_float(s[u]), __uint_as_float(s[8 + u]));
+          for (int u = 0; u < 8; ++u) mx[u] = __uint_as_float(s[u]);
 #pragma unroll
-          for (int j = 16; j < 128; j += 16)
+          for (int j = 8; j < 128; j += 8)
 #pragma unroll
-            for (int u = 0; u < 8; ++u) mx[u] = max3(mx[u], __uint_as_float(s[j + u]), __uint_as_float(s[j + 8 + u]));
-          const float m = fmaxf(max3(mx[0], mx[1], mx[2]), max3(max3(mx[3], mx[4], mx[5]), mx[6], mx[7]));
+            for (int u = 0; u < 8; ++u) mx[u] = fmaxf(mx[u], __uint_as_float(s[j + u]));
+          const float m = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])),
+                                fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
           AMP_PHASE(2);
-          // The two softmax warps of an SM sub-partition (one per warpgroup) take turns in the MUFU-bound phase, so
-          // that one's tcgen05.ld / max / tcgen05.st overlap the other's exponentials instead of both stalling on MUFU.
-          if (use_token) AMP_WAIT(&sm.tok[b][warp & 3], c & 1, 305);
-          AMP_PHASE(7);
-          // Exponentials in batches of 16, software-pipelined by hand: the sums and bf16 packs of batch k are issued
-          // behind the MUFUs of batch k+1, so that a single warp keeps the MUFU pipe busy (in-order issue would
-          // otherwise stall on every MUFU result).
-          float lsum[4] = {0.f, 0.f, 0.f, 0.f};
+          float l0 = 0.f, l1 = 0.f;
           uint32_t pk[64];
-          float ev[2][16];
 #pragma unroll
-          for (int u = 0; u < 16; ++u) ev[0][u] = ex2_approx_v(__uint_as_float(s[u]) - m);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            if (k + 1 < 8) {
-#pragma unroll
-              for (int u = 0; u < 16; ++u) ev[(k + 1) & 1][u] = ex2_approx_v(__uint_as_float(s[16 * (k + 1) + u]) - m);
-            }
-#pragma unroll
-            for (int u = 0; u < 16; u += 2) {
-              lsum[(u >> 1) & 3] += ev[k & 1][u] + ev[k & 1][u + 1];
-              pk[8 * k + (u >> 1)] = pack_bf16x2(ev[k & 1][u], ev[k & 1][u + 1]);
-            }
+          for (int j = 0; j < 64; ++j) {
+            const float e0 = ex2_approx(__uint_as_float(s[2 * j]) - m);
+            const float e1 = ex2_approx(__uint_as_float(s[2 * j + 1]) - m);
+            l0 += e0;
+            l1 += e1;
+            pk[j] = pack_bf16x2(e0, e1);
           }
-          __syncwarp();
-          if (use_token && lane == 0) mbar_arrive(&sm.tok[b ^ 1][warp & 3]);
-          const float l = (lsum[0] + lsum[1]) + (lsum[2] + lsum[3]);
+          const float l = l0 + l1;
           // normalise in bf16x2 so that the P V MMAs of all in-edges can accumulate into one TMEM tile
           const float inv_l = 1.0f / l;
           const uint32_t inv2 = pack_bf16x2(inv_l, inv_l);
@@ -423,13 +402,12 @@ static int attn_fwd_bf16_impl(const void* q, const void* k, const void* v,
   const size_t smem = sizeof(FwdSmem) + 1024;
   const int grid = (int)(N < sm_count() ? N : sm_count());
   const int hd = d / H;
-  static const int use_token = getenv("AMPCONV_FWD_TOKEN") ? atoi(getenv("AMPCONV_FWD_TOKEN")) : 1;
 #define AMP_LAUNCH_FWD(HDV, PROFV)                                                                                    \
   do {                                                                                                                \
     AMPCONV_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_bf16_kernel<HDV, PROFV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                           (int)smem));                                                                \
     attn_fwd_bf16_kernel<HDV, PROFV><<<grid, kFwdThreads, smem, stream>>>(mq, mk, mv, dst_rowptr, dst_src, inv_deg, order, \
-                                                                         counter, status, agg, lse2, (int)N, F, use_token, prof);  \
+                                                                         counter, status, agg, lse2, (int)N, F, prof);  \
   } while (0)
   if (hd == 16) {
     if (prof) AMP_LAUNCH_FWD(16, true); else AMP_LAUNCH_FWD(16, false);

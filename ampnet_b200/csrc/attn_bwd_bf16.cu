@@ -1,24 +1,28 @@
 // bf16 tensor-core family, backward: flash-style recompute of the per-edge attention from the saved
 // log-sum-exp (autograd of custom_multihead_attn_forward.py:4140-4186 + PyG scatter-mean, which the
 // reference gets from saved [E,H,F,F] probabilities).  Two persistent warp-specialised kernels built
-// from one template; both accumulate over a node's edges on chip (no atomics, deterministic):
+// from one template; both accumulate over a node's edges IN TENSOR MEMORY (no atomics, deterministic):
 //
 //   MODE_DQ  (destination-sorted): own tiles = Q'_t, dO_t (per destination), edge tiles = K_s, V_s.
 //       X = Q_h K_h^T, Y = dO_h V_h^T;  P = exp2(X - lse2_i), W = P o Y, delta_i = sum_j W_ij;
-//       TX = P K_h, TY = W K_h (A from TMEM, B = K tile as MN-major operand);
-//       dQ_h += TY - delta o TX.                      delta[p,h,i] is written for MODE_DKV.
+//       dQ_h = sum_e W_e K_h  -  sum_e delta_e o (P_e K_h):
+//       the first sum accumulates in TMEM over the node's edges; P_e K_h (16 columns per edge and head) goes to a
+//       small TMEM ring and is folded into registers two items later, when delta_e is known, so that no MMA
+//       operand ever waits for a row sum.  delta[p,h,i] is written for MODE_DKV.
 //   MODE_DKV (source-sorted): own tiles = K_s, V_s (per source), edge tiles = Q'_t, dO_t plus the
 //       lse2 / delta rows of the edge (bulk copies).  Everything is transposed (thread = source token):
 //       X = K_h Q_h^T, Y = V_h dO_h^T;  P^T = exp2(X - lse2_col), dS^T = P^T o (Y - delta_col);
-//       TX = P^T dO_h -> dV_h,  TY = dS^T Q'_h -> dK_h.
+//       dV_h += P^T dO_h,  dK_h += dS^T Q'_h, both accumulated in TMEM over the node's edges.
 //
-// Work split: an item = (edge, head).  Its two score tiles X, Y live in one of two TMEM sets (item parity:
-// columns [256s, 256s+256), X at +0, Y at +128), so the score MMAs of item c+1 run while item c is being
-// processed.  All 16 elementwise warps work on the same item (4 per SM sub-partition, to hide tcgen05.ld and
-// MUFU latency): warp w owns TMEM lane quarter w & 3 and score columns [32g, 32g+32), g = w >> 2.  The bf16
-// operands P / W (or P^T / dS^T) overwrite the first 16 columns of each group's own fp32 scores in place, so a
-// write can never pass another warp's read; TX / TY land in the 16-column holes at +16 (and +48 for hd = 32).
-// tcgen05 issue costs ~100 clk per instruction, so three converged warps issue: X/Y, TX and TY.
+// Work split: a half-item = (edge, head, half) covers 64 of the 128 score columns.  Its two fp32 score tiles
+// X | Y (64 + 64 columns) live in one of three TMEM sets (columns [128 s, 128 s + 128)); columns [384, 512) hold
+// the accumulators (MODE_DKV: dV | dK; MODE_DQ: dQ | the P K ring).  The 16 elementwise warps form two groups of
+// 8 that work on alternate half-items, so that one group's tcgen05.ld / st / barrier latencies overlap the other
+// group's exponentials (MUFU is the binding pipe: profiles/r01_softmax_pipe.log).  Warp w owns TMEM lane quarter
+// w & 3 and 32 score columns of its group's half-item; the bf16 operands overwrite the first 8 of every 16 fp32
+// score columns in place, so a write can never pass another warp's read.  Three converged warps issue
+// tcgen05.mma (~20 clk per instruction, profiles/r01_mma_cost.log): scores, consumers of the X-side operand,
+// consumers of the Y-side operand; a set is recycled as soon as both consumers have committed.
 #include <cuda_bf16.h>
 #include <math_constants.h>
 
@@ -32,9 +36,10 @@ using namespace umma;
 
 constexpr int kD = 64;
 constexpr int kTileBytes = 128 * 128;
-constexpr int kEwWarps = 16;     // elementwise warps: 4 TMEM lane quarters x 4 column groups of 32 score columns
-constexpr int kTWarps = 4;       // T-MMA issuing warps: (TX | TY) x (K steps 0-3 | 4-7)
-constexpr int kThreads = (kEwWarps + 2 + kTWarps) * 32;   // + producer warp + score-MMA warp + T warps
+constexpr int kEwWarps = 16;     // elementwise warps: 4 TMEM lane quarters x 4 column groups of 16 score columns
+constexpr int kThreads = (kEwWarps + 4) * 32;   // + producer warp + score-MMA warp + 2 consumer-MMA warps
+constexpr int kSets = 3;         // TMEM score sets of 128 columns
+constexpr int kAccCol = 384;     // accumulator block 0 at [384, 448), block 1 at [448, 512)
 constexpr int MODE_DQ = 0, MODE_DKV = 1;
 constexpr int kStatFloats = 4 * 128;   // H * roundup4(F) <= 512 floats per edge and statistic
 
@@ -44,16 +49,17 @@ struct NodeSlot {
 
 template <int MODE>
 struct BwdSmem {
-  static constexpr int NS = MODE == MODE_DQ ? 3 : 2;
-  static constexpr int NACC = MODE == MODE_DQ ? 1 : 2;
+  static constexpr int NS = 4;
   uint8_t own[2][2][kTileBytes];        // [slot][tile 0/1]
   uint8_t edge[NS][2][kTileBytes];      // [stage][tile 0/1]
-  float stat[NS][2][kStatFloats];       // MODE_DKV: lse2 / delta rows of the edge
-  float acc[NACC * 16][512];            // [accumulator element][elementwise thread]
+  float stat[MODE == MODE_DKV ? NS : 1][2][kStatFloats];   // MODE_DKV: lse2 / delta rows of the edge
+  float dl[4][4][128];                  // MODE_DQ: partial delta of [item & 3][group * 2 + column block][row]
   uint64_t own_full[2], own_empty[2];
   uint64_t edge_full[NS], edge_empty[NS];
-  uint64_t xy_full[2], xy_empty[2], u_full[2], t_full[2];
-  float dl[2][4][128];                  // MODE_DQ: partial delta of [set][column group][row]
+  uint64_t xy_full[kSets], set_empty[kSets], op_full[kSets];
+  uint64_t acc_full, acc_empty;
+  uint64_t dl_bar[4][4];                // MODE_DQ: [item & 3][lane quarter]: the quarter's four warps wrote their partial deltas
+  uint64_t ko_full[4], ko_empty[4];     // MODE_DQ: ring of P K results (slot = item % (64 / HD))
   NodeSlot slot[2];
   uint32_t tmem_base;
 };
@@ -76,7 +82,7 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
 
 // own0/own1: tensor maps of the per-node tiles, oth0/oth1: of the per-edge tiles.
 // rowptr/nbr: CSR of the pass (by destination for MODE_DQ, by source for MODE_DKV); slot_of[e] = position of
-// edge e in the statistics arrays (NULL: identity).  d_qkv: fp32 [rows, 192].
+// edge e in the statistics arrays (NULL: identity).  d_qkv: fp32 [rows, out_ld].
 template <int HD, int MODE, bool PROF>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_constant__ CUtensorMap own1,
@@ -93,21 +99,30 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Fs = (F + 3) & ~3;   // row stride of the statistics arrays
+  constexpr int W_SCORE = kEwWarps + 1, W_TX = kEwWarps + 2, W_TY = kEwWarps + 3;
 
-  if (warp == kEwWarps + 1) tmem_alloc(&sm.tmem_base, 512);
+  if (warp == W_SCORE) tmem_alloc(&sm.tmem_base, 512);
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sm.own_full[i], 1);
-      mbar_init(&sm.own_empty[i], 1 + kEwWarps + kTWarps);
+      mbar_init(&sm.own_empty[i], 1 + kEwWarps + 2);
+    }
+    for (int i = 0; i < kSets; ++i) {
       mbar_init(&sm.xy_full[i], 1);
-      mbar_init(&sm.xy_empty[i], kEwWarps);
-      mbar_init(&sm.u_full[i], kEwWarps);
-      mbar_init(&sm.t_full[i], kTWarps);
+      mbar_init(&sm.set_empty[i], 2);
+      mbar_init(&sm.op_full[i], kEwWarps / 2);
     }
     for (int i = 0; i < NS; ++i) {
       mbar_init(&sm.edge_full[i], 1);
-      mbar_init(&sm.edge_empty[i], MODE == MODE_DKV ? 1 + kTWarps + kEwWarps : 1 + kTWarps);
+      mbar_init(&sm.edge_empty[i], MODE == MODE_DKV ? 3 + kEwWarps : 3);
     }
+    for (int i = 0; i < 16; ++i) mbar_init(&sm.dl_bar[i >> 2][i & 3], 4);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&sm.ko_full[i], 1);
+      mbar_init(&sm.ko_empty[i], kEwWarps);
+    }
+    mbar_init(&sm.acc_full, 2);
+    mbar_init(&sm.acc_empty, kEwWarps);
     fence_barrier_init();
   }
   if (warp == kEwWarps && lane == 0) {
@@ -120,8 +135,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
-  const int nqk = ((F + 15) >> 4) << 4;
-  const int ksteps = (F + 15) >> 4;
+  const int nhalf = F > 64 ? 2 : 1;                  // halves with at least one valid score column
   const uint32_t stat_bytes = (uint32_t)(H * Fs * sizeof(float));
 
   if (warp == kEwWarps) {
@@ -196,69 +210,58 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       if (failed) AMP_FAIL(failed);
       if (node < 0) break;
     }
-  } else if (warp == kEwWarps + 1) {
-    // ------------------------------------------------------------------ score MMAs X, Y of every item
+  } else if (warp == W_SCORE) {
+    // ------------------------------------------------------------------ score MMAs X, Y of every half-item
     {
-      const uint32_t idesc_xy = idesc_bf16(128, nqk, 0, 0);
-      uint32_t qi = 0, edge = 0, c = 0;
-      const bool do_prof = PROF && blockIdx.x == 0;
-      long long pm[4] = {0, 0, 0, 0};
-      long long tp = do_prof ? clock64() : 0;
-#define AMP_MPHASE(i) do { if (do_prof) { const long long now_ = clock64(); pm[i] += now_ - tp; tp = now_; } } while (0)
+      const uint32_t idesc_xy = idesc_bf16(128, 64, 0, 0);
+      uint32_t qi = 0, edge = 0, k = 0;
       for (;; ++qi) {
         const uint32_t qb = qi & 1;
         AMP_WAIT(&sm.own_full[qb], (qi >> 1) & 1, 201);
         const NodeSlot ns = sm.slot[qb];
         if (ns.node < 0) break;
-        AMP_MPHASE(3);
         for (int e = ns.e_begin; e < ns.e_end; ++e, ++edge) {
           const uint32_t st = edge % NS;
           AMP_WAIT(&sm.edge_full[st], (edge / NS) & 1, 202);
-          AMP_MPHASE(0);
 #pragma unroll
-          for (int h = 0; h < H; ++h, ++c) {
-            const uint32_t set = c & 1;
-            AMP_WAIT(&sm.xy_empty[set], ((c >> 1) & 1) ^ 1, 203);
-            AMP_MPHASE(1);
-            tc_fence_after();
-            const uint32_t hb = h * (HD * 2);
-            const uint64_t a0 = smem_desc(smem_u32(sm.own[qb][0]) + hb, 16, 1024, LAYOUT_SW128);
-            const uint64_t a1 = smem_desc(smem_u32(sm.own[qb][1]) + hb, 16, 1024, LAYOUT_SW128);
-            const uint64_t b0 = smem_desc(smem_u32(sm.edge[st][0]) + hb, 16, 1024, LAYOUT_SW128);
-            const uint64_t b1 = smem_desc(smem_u32(sm.edge[st][1]) + hb, 16, 1024, LAYOUT_SW128);
+          for (int h = 0; h < H; ++h) {
+            for (int half = 0; half < nhalf; ++half, ++k) {
+              const uint32_t set = k % kSets;
+              AMP_WAIT(&sm.set_empty[set], ((k / kSets) & 1) ^ 1, 203);
+              tc_fence_after();
+              const uint32_t hb = h * (HD * 2);
+              const uint64_t a0 = smem_desc(smem_u32(sm.own[qb][0]) + hb, 16, 1024, LAYOUT_SW128);
+              const uint64_t a1 = smem_desc(smem_u32(sm.own[qb][1]) + hb, 16, 1024, LAYOUT_SW128);
+              // B = rows [64 half, 64 half + 64) of the edge tiles (8 swizzle atoms of 8 rows = 8192 bytes)
+              const uint64_t b0 = smem_desc(smem_u32(sm.edge[st][0]) + half * 8192 + hb, 16, 1024, LAYOUT_SW128);
+              const uint64_t b1 = smem_desc(smem_u32(sm.edge[st][1]) + half * 8192 + hb, 16, 1024, LAYOUT_SW128);
 #pragma unroll
-            for (int ks = 0; ks < HD / 16; ++ks)
-              mma_ss_w(tmem + set * 256, desc_advance(a0, ks * 32), desc_advance(b0, ks * 32), idesc_xy, ks > 0);
+              for (int ks = 0; ks < HD / 16; ++ks)
+                mma_ss_w(tmem + set * 128, desc_advance(a0, ks * 32), desc_advance(b0, ks * 32), idesc_xy, ks > 0);
 #pragma unroll
-            for (int ks = 0; ks < HD / 16; ++ks)
-              mma_ss_w(tmem + set * 256 + 128, desc_advance(a1, ks * 32), desc_advance(b1, ks * 32), idesc_xy, ks > 0);
-            mma_commit_w(&sm.xy_full[set]);
-            AMP_MPHASE(2);
+              for (int ks = 0; ks < HD / 16; ++ks)
+                mma_ss_w(tmem + set * 128 + 64, desc_advance(a1, ks * 32), desc_advance(b1, ks * 32), idesc_xy, ks > 0);
+              mma_commit_w(&sm.xy_full[set]);
+            }
           }
           mma_commit_w(&sm.edge_empty[st]);
           if (e + 1 == ns.e_end) mma_commit_w(&sm.own_empty[qb]);
         }
       }
-      if (do_prof && lane == 0) {
-        for (int i = 0; i < 4; ++i) prof[32 + i] = pm[i];
-        prof[36] = c;
-      }
-#undef AMP_MPHASE
     }
-  } else if (warp >= kEwWarps + 2) {
-    // ------------------------------------------------------------------ T MMAs: one warp issues TX = X' * B_tx, the other TY = Y' * B_ty
-    //   (A = the bf16 operand the elementwise warps wrote back into TMEM, B = an edge tile as MN-major operand)
+  } else if (warp == W_TX || warp == W_TY) {
+    // ------------------------------------------------------------------ consumer MMAs
+    //   which = 0: X-side operand (MODE_DQ: P, MODE_DKV: P^T), which = 1: Y-side operand (W / dS^T)
+    //   B = an edge tile as MN-major operand: K / K (MODE_DQ), dO / Q' (MODE_DKV)
+    //   destination: MODE_DKV block `which` of the node accumulators; MODE_DQ which = 1 the dQ accumulator,
+    //   which = 0 the P K ring slot of the item (fresh per item, folded by the elementwise warps).
     {
-      const uint32_t tw = warp - (kEwWarps + 2);
-      const uint32_t which = tw >> 1;                          // 0: TX, 1: TY
-      const int ks0 = 4 * (tw & 1);                            // this warp's K steps: [ks0, ks0 + 4)
+      const uint32_t which = warp == W_TY ? 1u : 0u;
       const uint32_t idesc_t = idesc_bf16(128, 16, 0, 1);      // N = 16 per MMA (two per K step when hd = 32)
-      const int btile = (which == 0 && MODE == MODE_DKV) ? 1 : 0;   // TX of the dK/dV pass multiplies dO; all others tile 0
-      uint32_t qi = 0, edge = 0, c = 0;
-      const bool do_prof = PROF && blockIdx.x == 0 && tw == 0;
-      long long pm[4] = {0, 0, 0, 0};
-      long long tp = do_prof ? clock64() : 0;
-#define AMP_TPHASE(i) do { if (do_prof) { const long long now_ = clock64(); pm[i] += now_ - tp; tp = now_; } } while (0)
+      const int btile = (which == 0 && MODE == MODE_DKV) ? 1 : 0;
+      const bool ring = MODE == MODE_DQ && which == 0;
+      constexpr int R = 64 / HD;                                // ring slots
+      uint32_t qi = 0, edge = 0, k = 0, item = 0;
       for (;; ++qi) {
         const uint32_t qb = qi & 1;
         AMP_WAIT(&sm.own_full[qb], (qi >> 1) & 1, 211);
@@ -266,55 +269,55 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.own_empty[qb]);
         if (ns.node < 0) break;
+        // the accumulators of the previous node must have been read back
+        AMP_WAIT(&sm.acc_empty, (qi & 1) ^ 1, 212);
         for (int e = ns.e_begin; e < ns.e_end; ++e, ++edge) {
           const uint32_t st = edge % NS;
+          const uint32_t keep = ring ? 0u : (e != ns.e_begin ? 1u : 0u);
 #pragma unroll
-          for (int h = 0; h < H; ++h, ++c) {
-            const uint32_t set = c & 1;
-            AMP_TPHASE(3);
-            AMP_WAIT(&sm.u_full[set], (c >> 1) & 1, 213);
-            AMP_TPHASE(0);
-            tc_fence_after();
-            const uint32_t a_col = tmem + set * 256 + which * 128;
+          for (int h = 0; h < H; ++h, ++item) {
             const uint64_t bd = smem_desc(smem_u32(sm.edge[st][btile]) + h * (HD * 2), 16, 1024, LAYOUT_SW128);
-            // every T MMA accumulates: the elementwise warps zeroed the T tiles, so the K steps of one tile may be
-            // issued by two warps in any order
+            const uint32_t slot = item % R;
+            const uint32_t d_col = ring ? tmem + kAccCol + 64 + slot * HD
+                                        : tmem + kAccCol + (MODE == MODE_DKV ? which * 64 : 0) + h * HD;
+            if (ring) AMP_WAIT(&sm.ko_empty[slot], ((item / R) & 1) ^ 1, 214);
+            for (int half = 0; half < nhalf; ++half, ++k) {
+              const uint32_t set = k % kSets;
+              AMP_WAIT(&sm.op_full[set], (k / kSets) & 1, 213);
+              tc_fence_after();
+              const uint32_t a_col = tmem + set * 128 + which * 64;
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const int ks = ks0 + kk;
-              if (ks < ksteps) {
-                const uint32_t a_addr = a_col + 32 * (ks >> 1) + 8 * (ks & 1);
+              for (int ks = 0; ks < 4; ++ks) {
+                if (64 * half + 16 * ks < F) {
+                  const uint32_t acc = (half | ks) ? 1u : keep;
 #pragma unroll
-                for (int half = 0; half < HD / 16; ++half)
-                  mma_ts_w(a_col + 16 + 32 * half, a_addr, desc_advance(bd, ks * 2048 + half * 32), idesc_t, 1u);
+                  for (int part = 0; part < HD / 16; ++part)
+                    mma_ts_w(d_col + 16 * part, a_col + 16 * ks, desc_advance(bd, (4 * half + ks) * 2048 + part * 32), idesc_t, acc);
+                }
               }
+              mma_commit_w(&sm.set_empty[set]);
             }
-            mma_commit_w(&sm.t_full[set]);
-            AMP_TPHASE(1);
-            if (do_prof) {
-              AMP_WAIT(&sm.t_full[set], (c >> 1) & 1, 214);   // observe only: how long until all four T warps' MMAs have landed
-              AMP_TPHASE(2);
-            }
+            if (ring) mma_commit_w(&sm.ko_full[slot]);
           }
           mma_commit_w(&sm.edge_empty[st]);
         }
+        mma_commit_w(&sm.acc_full);
       }
-      if (do_prof && lane == 0) {
-        for (int i = 0; i < 4; ++i) prof[40 + i] = pm[i];
-        prof[44] = c;
-      }
-#undef AMP_TPHASE
     }
   } else {
     // ------------------------------------------------------------------ elementwise warps
-    const uint32_t g = warp >> 2;                   // column group: score columns [32g, 32g+32)
-    const int row = (warp & 3) * 32 + lane;
+    const uint32_t q4 = warp & 3;                   // TMEM lane quarter
+    const uint32_t grp = warp >> 3;                 // group: works on half-items with k & 1 == grp
+    const uint32_t cb = (warp >> 2) & 1;            // column block: score columns [32cb, 32cb+32) of the half
+    const uint32_t j4 = grp * 2 + cb;               // 0..3 within the lane quarter
+    const int row = q4 * 32 + lane;
     const bool row_ok = row < F;
-    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    constexpr int HQ = HD / 4;                      // T columns this thread reads back per head
-    uint32_t qi = 0, c = 0, ei = 0;
-    float* acc = &sm.acc[0][threadIdx.x];           // element x of this thread: acc[x * 512]
-    const bool do_prof = PROF && blockIdx.x == 0 && (warp == 0 || warp == kEwWarps - 1);
+    const uint32_t lane_base = tmem + ((uint32_t)(q4 * 32) << 16);
+    constexpr int R = 64 / HD;                      // P K ring slots (MODE_DQ)
+    constexpr int HQ = HD / 4;                      // P K / dQ columns per head owned by this thread (MODE_DQ)
+    constexpr int DEFER = 2;                        // MODE_DQ: items between publishing P and folding delta o (P K)
+    uint32_t qi = 0, k = 0, ei = 0, item = 0;
+    const bool do_prof = PROF && blockIdx.x == 0 && warp == 0;
     long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tp = do_prof ? clock64() : 0;
 #define AMP_PHASE(i) do { if (do_prof) { const long long now_ = clock64(); pt[i] += now_ - tp; tp = now_; } } while (0)
@@ -326,168 +329,191 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.own_empty[qb]);
       if (ns.node < 0) break;
+      float racc[H][HQ];                             // MODE_DQ: - sum_e delta_e o (P_e K_h), this thread's columns
 #pragma unroll
-      for (int x = 0; x < Smem::NACC * H * HQ; ++x) acc[x * 512] = 0.f;
-      uint32_t t = 0;
-      int e_prev = 0;
-      // folds this thread's HQ columns of TX / TY of item cc (head hp, edge slot ep) into the accumulators, frees the set
-      auto readback = [&](uint32_t cc, int hp, int ep) -> bool {
-        const uint32_t set = cc & 1;
-        if (!mbar_wait(&sm.t_full[set], (cc >> 1) & 1)) return false;
-        AMP_PHASE(3);
+      for (int h = 0; h < H; ++h)
+#pragma unroll
+        for (int x = 0; x < HQ; ++x) racc[h][x] = 0.f;
+      uint32_t t = 0;                                // items of this node processed so far
+      // MODE_DQ: folds item `it` (head hp, the t-th... of this node at edge slot ep) into racc and frees its ring slot
+      auto fold = [&](uint32_t it, int hp, int ep) -> bool {
+        const uint32_t slot = it % R;
+        if (!mbar_wait(&sm.dl_bar[it & 3][q4], (it >> 2) & 1)) return false;
+        if (!mbar_wait(&sm.ko_full[slot], (it / R) & 1)) return false;
         tc_fence_after();
-        uint32_t tx[HQ], ty[HQ];
-        // logical T column HQ*g maps to +16 + col (hd = 16) or to the two 16-column holes +16 / +48 (hd = 32)
-        const uint32_t tcol = HQ * g;
-        const uint32_t base = lane_base + set * 256 + (tcol < 16 ? 16 + tcol : 48 + (tcol - 16));
-        if constexpr (HQ == 4) {
-          tmem_ld_32x32b_x4(base, tx);
-          tmem_ld_32x32b_x4(base + 128, ty);
-        } else {
-          tmem_ld_32x32b_x8(base, tx);
-          tmem_ld_32x32b_x8(base + 128, ty);
-        }
+        uint32_t ko[HQ];
+        if constexpr (HQ == 4) tmem_ld_32x32b_x4(lane_base + kAccCol + 64 + slot * HD + HQ * j4, ko);
+        else tmem_ld_32x32b_x8(lane_base + kAccCol + 64 + slot * HD + HQ * j4, ko);
+        const float* dls = &sm.dl[it & 3][0][row];
+        const float dsum = (dls[0] + dls[128]) + (dls[256] + dls[384]);
         tmem_ld_wait();
-        float dl = 0.f;
-        if (MODE == MODE_DQ) dl = (sm.dl[set][0][row] + sm.dl[set][1][row]) + (sm.dl[set][2][row] + sm.dl[set][3][row]);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.xy_empty[set]);
-        float* a = acc + hp * HQ * 512;
-        if (MODE == MODE_DQ) {
-          if (g == 0 && row_ok) delta[((int64_t)ep * H + hp) * Fs + row] = dl;
+        if (lane == 0) mbar_arrive(&sm.ko_empty[slot]);
+        if (j4 == 0 && row_ok) delta[((int64_t)ep * H + hp) * Fs + row] = dsum;
 #pragma unroll
-          for (int x = 0; x < HQ; ++x) a[x * 512] += __uint_as_float(ty[x]) - dl * __uint_as_float(tx[x]);
-        } else {
-          float* a2 = a + H * HQ * 512;
-#pragma unroll
-          for (int x = 0; x < HQ; ++x) {
-            a[x * 512] += __uint_as_float(ty[x]);    // dK
-            a2[x * 512] += __uint_as_float(tx[x]);   // dV
-          }
-        }
-        AMP_PHASE(4);
+        for (int x = 0; x < HQ; ++x) racc[hp][x] -= dsum * __uint_as_float(ko[x]);
         return true;
       };
       for (int e = ns.e_begin; e < ns.e_end; ++e, ++ei) {
         const uint32_t st = ei % NS;
         if (MODE == MODE_DKV) AMP_WAIT(&sm.edge_full[st], (ei / NS) & 1, 306);   // acquire the bulk-copied statistics rows
 #pragma unroll
-        for (int h = 0; h < H; ++h) {
-          const uint32_t set = c & 1;
+        for (int h = 0; h < H; ++h, ++item, ++t) {
           float L = 0.f;
-          if (MODE == MODE_DQ) L = row_ok ? lse2[((int64_t)e * H + h) * Fs + row] : 0.f;
+          if (MODE == MODE_DQ) {
+            L = row_ok ? lse2[((int64_t)e * H + h) * Fs + row] : 0.f;
+            if (t >= DEFER) {
+              // item - DEFER belongs to this node: head (h - DEFER) mod H, edge slot e or e - 1
+              constexpr int dh = DEFER % H;
+              const int hp = (h + H - dh) % H;
+              const int ep = e - (DEFER + H - 1 - h) / H;
+              if (!fold(item - DEFER, hp, ep)) AMP_FAIL(308);
+            }
+          }
+          const float* Ls = sm.stat[MODE == MODE_DKV ? st : 0][0] + h * Fs;
+          const float* Ds = sm.stat[MODE == MODE_DKV ? st : 0][1] + h * Fs;
+          float dl = 0.f;
           AMP_PHASE(5);
-          AMP_WAIT(&sm.xy_full[set], (c >> 1) & 1, 302);
-          AMP_PHASE(0);
-          tc_fence_after();
-          const float* Ls = sm.stat[st][0] + h * Fs;
-          const float* Ds = sm.stat[st][1] + h * Fs;
-          const uint32_t xbase = lane_base + set * 256 + 32 * g;
-          float dl0 = 0.f, dl1 = 0.f;
+          for (int half = 0; half < nhalf; ++half, ++k) {
+            if ((k & 1) != grp) continue;
+            const uint32_t set = k % kSets;
+            AMP_WAIT(&sm.xy_full[set], (k / kSets) & 1, 302);
+            AMP_PHASE(0);
+            tc_fence_after();
+            const uint32_t xbase = lane_base + set * 128 + 32 * cb;
+            uint32_t xs[2][16], ys[2][16];
+            tmem_ld_32x32b_x16(xbase, xs[0]);
+            tmem_ld_32x32b_x16(xbase + 64, ys[0]);
+            tmem_ld_32x32b_x16(xbase + 16, xs[1]);
+            tmem_ld_32x32b_x16(xbase + 64 + 16, ys[1]);
+            tmem_ld_wait();
 #pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            const int col0 = 32 * g + 16 * k;          // first score column of this sub-chunk
-            if (col0 < nqk) {
-              uint32_t xs[16], ys[16];
-              tmem_ld_32x32b_x16(xbase + 16 * k, xs);
-              tmem_ld_32x32b_x16(xbase + 128 + 16 * k, ys);
-              tmem_ld_wait();
+            for (int ch = 0; ch < 2; ++ch) {
               uint32_t px[8], py[8];
+              const int col0 = 64 * half + 32 * cb + 16 * ch;     // first score column of this chunk
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const int c0 = col0 + 2 * j;
                 float p0, p1, u0, u1;
                 if (MODE == MODE_DQ) {
-                  p0 = ex2_approx(__uint_as_float(xs[2 * j]) - L);
-                  p1 = ex2_approx(__uint_as_float(xs[2 * j + 1]) - L);
-                  u0 = p0 * __uint_as_float(ys[2 * j]);
-                  u1 = p1 * __uint_as_float(ys[2 * j + 1]);
+                  p0 = ex2_approx(__uint_as_float(xs[ch][2 * j]) - L);
+                  p1 = ex2_approx(__uint_as_float(xs[ch][2 * j + 1]) - L);
+                  u0 = p0 * __uint_as_float(ys[ch][2 * j]);
+                  u1 = p1 * __uint_as_float(ys[ch][2 * j + 1]);
                 } else {
                   const float2 l2 = *reinterpret_cast<const float2*>(Ls + c0);
                   const float2 d2 = *reinterpret_cast<const float2*>(Ds + c0);
-                  p0 = ex2_approx(__uint_as_float(xs[2 * j]) - l2.x);
-                  p1 = ex2_approx(__uint_as_float(xs[2 * j + 1]) - l2.y);
-                  u0 = p0 * (__uint_as_float(ys[2 * j]) - d2.x);
-                  u1 = p1 * (__uint_as_float(ys[2 * j + 1]) - d2.y);
+                  p0 = ex2_approx(__uint_as_float(xs[ch][2 * j]) - l2.x);
+                  p1 = ex2_approx(__uint_as_float(xs[ch][2 * j + 1]) - l2.y);
+                  u0 = p0 * (__uint_as_float(ys[ch][2 * j]) - d2.x);
+                  u1 = p1 * (__uint_as_float(ys[ch][2 * j + 1]) - d2.y);
                 }
                 if (F < 128) {
                   if (c0 >= F) { p0 = 0.f; u0 = 0.f; }
                   if (c0 + 1 >= F) { p1 = 0.f; u1 = 0.f; }
                 }
-                dl0 += u0;
-                dl1 += u1;
+                dl += u0 + u1;
                 px[j] = pack_bf16x2(p0, p1);
                 py[j] = pack_bf16x2(u0, u1);
               }
-              // packed columns +8k of this group's own 32 columns: always behind this thread's own reads
-              tmem_st_32x32b_x8(xbase + 8 * k, px);
-              tmem_st_32x32b_x8(xbase + 128 + 8 * k, py);
+              // packed operands go to the first 8 of the chunk's own 16 columns: always behind this thread's own reads
+              tmem_st_32x32b_x8(xbase + 16 * ch, px);
+              tmem_st_32x32b_x8(xbase + 64 + 16 * ch, py);
             }
-            // Half way through the item the previous item's T tiles are complete: fold them in now and release its
-            // TMEM set, so that the score MMAs of the next item are issued while the second sub-chunk is processed.
-            if (k == 0 && t > 0) {
-              if (!readback(c - 1, (h + H - 1) % H, e_prev)) AMP_FAIL(304);
-            }
+            AMP_PHASE(1);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.op_full[set]);
+            AMP_PHASE(2);
           }
-          // zero the T tiles of this set (they live in the second half of this group's own, already consumed, score columns)
-          if (g < HD / 16) {
-            const uint32_t z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-            tmem_st_32x32b_x16(xbase + 16, z);
-            tmem_st_32x32b_x16(xbase + 128 + 16, z);
+          if (MODE == MODE_DQ) {
+            // partial delta of this warp's columns (zero when the item had no half-item for this group)
+            sm.dl[item & 3][j4][row] = dl;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.dl_bar[item & 3][q4]);
+            AMP_PHASE(3);
           }
-          if (MODE == MODE_DQ) sm.dl[set][g][row] = dl0 + dl1;
-          AMP_PHASE(1);
-          tmem_st_wait();
-          tc_fence_before();
+        }
+        if (MODE == MODE_DKV) {
           __syncwarp();
-          if (lane == 0) mbar_arrive(&sm.u_full[set]);
-          if (MODE == MODE_DKV && h == H - 1) {
-            if (lane == 0) mbar_arrive(&sm.edge_empty[st]);   // this warp no longer reads the stage's statistics rows
-          }
-          AMP_PHASE(2);
-          e_prev = e;
-          ++c;
-          ++t;
+          if (lane == 0) mbar_arrive(&sm.edge_empty[st]);   // this warp no longer reads the stage's statistics rows
         }
       }
-      if (t > 0) {
-        if (!readback(c - 1, H - 1, e_prev)) AMP_FAIL(305);
+      if (MODE == MODE_DQ) {
+        // drain: the last min(t, DEFER) items of the node (heads H-2, H-1 of the last edge for H = 4; 0, 1 for H = 2)
+#pragma unroll
+        for (int back = DEFER; back >= 1; --back) {
+          if (t >= (uint32_t)back) {
+            const int hp = (H * DEFER - back) % H;
+            const int ep = ns.e_end - 1 - (back - 1) / H;
+            if (!fold(item - back, hp, ep)) AMP_FAIL(309);
+          }
+        }
+        AMP_PHASE(4);
       }
-      if (row_ok) {
-        float* o = d_qkv + ((int64_t)ns.node * F + row) * out_ld;
+      // node epilogue: all consumer MMAs of the node have landed in the accumulators
+      AMP_WAIT(&sm.acc_full, qi & 1, 304);
+      AMP_PHASE(6);
+      tc_fence_after();
+      if (MODE == MODE_DQ) {
+        // dQ = TMEM accumulator (sum_e W_e K) + racc; this thread owns columns [h HD + HQ j4, + HQ) of every head
+        uint32_t a[H][HQ];
 #pragma unroll
         for (int h = 0; h < H; ++h) {
-          const float* a = acc + h * HQ * 512;
-          float4* o0 = reinterpret_cast<float4*>(o + out_c0 + h * HD + HQ * g);
+          if constexpr (HQ == 4) tmem_ld_32x32b_x4(lane_base + kAccCol + h * HD + HQ * j4, a[h]);
+          else tmem_ld_32x32b_x8(lane_base + kAccCol + h * HD + HQ * j4, a[h]);
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.acc_empty);
+        if (row_ok) {
+          float* o = d_qkv + ((int64_t)ns.node * F + row) * out_ld + out_c0 + HQ * j4;
 #pragma unroll
-          for (int x = 0; x < HQ; x += 4)
-            o0[x >> 2] = make_float4(a[x * 512] * out_scale0, a[(x + 1) * 512] * out_scale0,
-                                     a[(x + 2) * 512] * out_scale0, a[(x + 3) * 512] * out_scale0);
-          if (MODE == MODE_DKV) {
-            const float* a2 = a + H * HQ * 512;
-            float4* o1 = reinterpret_cast<float4*>(o + out_c1 + h * HD + HQ * g);
+          for (int h = 0; h < H; ++h) {
+            float4* o4 = reinterpret_cast<float4*>(o + h * HD);
 #pragma unroll
             for (int x = 0; x < HQ; x += 4)
-              o1[x >> 2] = make_float4(a2[x * 512] * out_scale1, a2[(x + 1) * 512] * out_scale1,
-                                       a2[(x + 2) * 512] * out_scale1, a2[(x + 3) * 512] * out_scale1);
+              o4[x >> 2] = make_float4((__uint_as_float(a[h][x]) + racc[h][x]) * out_scale0,
+                                       (__uint_as_float(a[h][x + 1]) + racc[h][x + 1]) * out_scale0,
+                                       (__uint_as_float(a[h][x + 2]) + racc[h][x + 2]) * out_scale0,
+                                       (__uint_as_float(a[h][x + 3]) + racc[h][x + 3]) * out_scale0);
           }
+        }
+      } else {
+        // block 0 = dV (X-side operand P^T), block 1 = dK (Y-side operand dS^T); this warp owns 32 of the 128 columns
+        uint32_t a[32];
+        tmem_ld_32x32b_x32(lane_base + kAccCol + 32 * j4, a);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.acc_empty);
+        if (row_ok) {
+          const bool is_dv = j4 < 2;
+          const float sc = is_dv ? out_scale1 : out_scale0;
+          float4* o = reinterpret_cast<float4*>(d_qkv + ((int64_t)ns.node * F + row) * out_ld +
+                                                (is_dv ? out_c1 : out_c0) + 32 * (j4 & 1));
+#pragma unroll
+          for (int x = 0; x < 32; x += 4)
+            o[x >> 2] = make_float4(__uint_as_float(a[x]) * sc, __uint_as_float(a[x + 1]) * sc,
+                                    __uint_as_float(a[x + 2]) * sc, __uint_as_float(a[x + 3]) * sc);
         }
       }
       AMP_PHASE(7);
       ++qi;
     }
     if (do_prof && lane == 0) {
-      long long* pr = prof + (warp == 0 ? 0 : 16);
-      for (int i = 0; i < 8; ++i) pr[i] = pt[i];
-      pr[8] = c;
+      for (int i = 0; i < 8; ++i) prof[i] = pt[i];
+      prof[8] = item;
     }
 #undef AMP_PHASE
   }
 fail:
   tc_fence_before();
   __syncthreads();
-  if (warp == kEwWarps + 1) tmem_dealloc(tmem, 512);
+  if (warp == W_SCORE) tmem_dealloc(tmem, 512);
 }
 
 long long* g_bwd_prof = nullptr;   // debug: set through ampconv_debug_set_bwd_profile
@@ -599,8 +625,9 @@ extern "C" int ampconv_attn_bwd_dkv_bf16_part(const void* q, const void* k, cons
 }
 
 // Debug: when set to a device buffer of 64 int64, the next backward launches run the instrumented kernel and fill it
-// with the cycles one elementwise warp spent per phase (wait X/Y, chunks, publish, wait T, fold T, stats load,
-// node wait, node epilogue) and its item count.  NULL restores the product kernels.
+// with the cycles elementwise warp 0 of CTA 0 spent per phase (wait X/Y, compute, publish, delta exchange, second
+// operand publish, statistics load, node / accumulator wait, node epilogue) and its item count.  NULL restores the
+// product kernels.
 extern "C" int ampconv_debug_set_bwd_profile(long long* prof) {
   ampconv::g_bwd_prof = prof;
   return AMPCONV_OK;

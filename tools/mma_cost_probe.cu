@@ -94,6 +94,69 @@ __global__ void __launch_bounds__(128) commit_kernel(long long* out) {
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// Mixed stream as in the backward kernels: per iteration 2 SS MMAs (N = 64, scores) + 8 TS MMAs (N = 16, consumers),
+// optionally with a commit after each group.  Reveals any cost of switching instruction descriptors.
+template <int PATTERN>
+__global__ void __launch_bounds__(128) mixed_kernel(long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar, bars[4];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 65536 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) { mbar_init(&bar, 1); for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1); fence_barrier_init(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (warp == 1) {
+    constexpr uint32_t id_ss = idesc_bf16(128, 64, 0, 0), id_ts = idesc_bf16(128, 16, 0, 1);
+    const uint64_t da = smem_desc(smem_u32(smem), 16, 1024, LAYOUT_SW128);
+    const uint64_t db = smem_desc(smem_u32(smem + 32768), 16, 1024, LAYOUT_SW128);
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < 32; ++it) {
+      if (PATTERN == 0 || PATTERN == 2) {       // 2 SS then 8 TS
+        mma_ss_w(tmem, da, db, id_ss, 0);
+        mma_ss_w(tmem + 64, da, db, id_ss, 0);
+        if (PATTERN == 2) mma_commit_w(&bars[0]);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) mma_ts_w(tmem + 384 + 16 * (u >> 2), tmem + 256 + 8 * (u & 3), desc_advance(db, (u & 3) * 2048), id_ts, 1);
+        if (PATTERN == 2) mma_commit_w(&bars[1]);
+      } else if (PATTERN == 1) {                // fully interleaved: SS, 4 TS, SS, 4 TS
+        mma_ss_w(tmem, da, db, id_ss, 0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) mma_ts_w(tmem + 384, tmem + 256 + 8 * u, desc_advance(db, u * 2048), id_ts, 1);
+        mma_ss_w(tmem + 64, da, db, id_ss, 0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) mma_ts_w(tmem + 400, tmem + 256 + 8 * u, desc_advance(db, u * 2048), id_ts, 1);
+      }
+    }
+    const long long t1 = clock64();
+    mma_commit_w(&bar);
+    mbar_wait(&bar, 0);
+    const long long t2 = clock64();
+    if (tid == 32) { out[0] = t1 - t0; out[1] = t2 - t0; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+template <int PATTERN>
+void run_mixed(const char* name, long long* dout) {
+  const size_t smem = 65536 + 1024;
+  CK(cudaFuncSetAttribute(mixed_kernel<PATTERN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  for (int rep = 0; rep < 2; ++rep) mixed_kernel<PATTERN><<<1, 128, smem>>>(dout);
+  CK(cudaDeviceSynchronize());
+  long long h[2];
+  CK(cudaMemcpy(h, dout, 16, cudaMemcpyDeviceToHost));
+  printf("RESULT mixed %-34s: issue %7.1f clk, issue+complete %7.1f clk per group of 2 SS(N=64) + 8 TS(N=16)\n", name,
+         h[0] / 32.0, h[1] / 32.0);
+}
+
 template <bool SS, int N, int NACC>
 void run(long long* dout) {
   const size_t smem = 65536 + 1024;
@@ -130,6 +193,9 @@ int main() {
   run<true, 64, 1>(dout); run<true, 64, 2>(dout);
   run<true, 128, 1>(dout); run<true, 128, 2>(dout);
   run<true, 256, 1>(dout);
+  run_mixed<0>("2 SS then 8 TS", dout);
+  run_mixed<1>("SS, 4 TS, SS, 4 TS", dout);
+  run_mixed<2>("2 SS, commit, 8 TS, commit", dout);
   run_commit<16, 1>(dout); run_commit<16, 2>(dout); run_commit<16, 4>(dout); run_commit<16, 8>(dout);
   run_commit<128, 1>(dout); run_commit<128, 2>(dout);
   return 0;

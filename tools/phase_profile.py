@@ -56,7 +56,8 @@ def bwd():
     _lib.call("ampconv_attn_fwd_bf16", q, k, v, g.dst_rowptr, g.dst_src, g.inv_deg, None, agg, lse2, *tail)
     prof = torch.zeros(64, dtype=torch.int64, device=dev)
     lib = _lib.load()
-    names = ["wait X/Y", "chunks (ld, exp, pack, st)", "publish", "wait T", "fold T", "stats/lse load", "node wait", "node epilogue"]
+    names = ["wait X/Y", "compute (ld, exp, pack, st)", "publish", "delta exchange", "scale P + publish", "lse load", "node / accumulator wait",
+             "node epilogue"]
     for mode in ("dq", "dkv"):
         prof.zero_()
         lib.ampconv_debug_set_bwd_profile(ctypes.c_void_p(prof.data_ptr()))
