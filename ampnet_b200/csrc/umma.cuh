@@ -73,16 +73,28 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or the hint (ns) elapses,
+// instead of returning after a short system-dependent slice -- a waiting warp then costs (almost) no issue slots.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
 // Waits until the phase with the given parity completes.  The wait is bounded (budget_ns of wall
 // time, default 0.25 s) so that a protocol bug turns into a reported failure (returns false)
 // instead of a hung GPU; legitimate waits in these kernels last microseconds.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, uint64_t budget_ns = 250000000ull) {
-  for (int i = 0; i < 1024; ++i)
-    if (mbar_try_wait(bar, parity)) return true;
+  if (mbar_try_wait(bar, parity)) return true;
   const uint64_t t0 = global_timer_ns();
+#pragma unroll 1
   for (;;) {
-    for (int i = 0; i < 256; ++i)
-      if (mbar_try_wait(bar, parity)) return true;
+    if (mbar_try_wait_hint(bar, parity, 200000u)) return true;
     if (global_timer_ns() - t0 > budget_ns) return false;
   }
 }
