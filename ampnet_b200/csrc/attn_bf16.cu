@@ -282,26 +282,32 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
             for (int j = 0; j < 128; ++j)
               if (j >= F) s[j] = __float_as_uint(-CUDART_INF_F);
           }
+          // row max: 8 chains of 3-input max (FMNMX3)
           float mx[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) mx[u] = __uint_as_float(s[u]);
+          for (int u = 0; u < 8; ++u) mx[u] = fmaxf(__uint_as_float(s[u]), __uint_as_float(s[8 + u]));
 #pragma unroll
-          for (int j = 8; j < 128; j += 8)
+          for (int j = 16; j < 128; j += 16)
 #pragma unroll
-            for (int u = 0; u < 8; ++u) mx[u] = fmaxf(mx[u], __uint_as_float(s[j + u]));
-          const float m = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])),
-                                fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
+            for (int u = 0; u < 8; ++u) mx[u] = max3(mx[u], __uint_as_float(s[j + u]), __uint_as_float(s[j + 8 + u]));
+          const float m = fmaxf(max3(mx[0], mx[1], mx[2]), max3(max3(mx[3], mx[4], mx[5]), mx[6], mx[7]));
           AMP_PHASE(2);
-          float l0 = 0.f, l1 = 0.f;
+          // exponentials: subtract and row sum as packed fp32 pairs (FADD2: half the issue slots of scalar FADD)
+          float2 la = make_float2(0.f, 0.f), lb = la;
+          const float2 nm = make_float2(-m, -m);
           uint32_t pk[64];
 #pragma unroll
-          for (int j = 0; j < 64; ++j) {
-            const float e0 = ex2_approx(__uint_as_float(s[2 * j]) - m);
-            const float e1 = ex2_approx(__uint_as_float(s[2 * j + 1]) - m);
-            l0 += e0;
-            l1 += e1;
-            pk[j] = pack_bf16x2(e0, e1);
+          for (int j = 0; j < 64; j += 2) {
+            const float2 a2 = f2add(make_float2(__uint_as_float(s[2 * j]), __uint_as_float(s[2 * j + 1])), nm);
+            const float2 b2 = f2add(make_float2(__uint_as_float(s[2 * j + 2]), __uint_as_float(s[2 * j + 3])), nm);
+            const float2 ea = make_float2(ex2_approx(a2.x), ex2_approx(a2.y));
+            const float2 eb = make_float2(ex2_approx(b2.x), ex2_approx(b2.y));
+            la = f2add(la, ea);
+            lb = f2add(lb, eb);
+            pk[j] = pack_bf16x2(ea.x, ea.y);
+            pk[j + 1] = pack_bf16x2(eb.x, eb.y);
           }
+          const float l0 = la.x + la.y, l1 = lb.x + lb.y;
           const float l = l0 + l1;
           // normalise in bf16x2 so that the P V MMAs of all in-edges can accumulate into one TMEM tile
           const float inv_l = 1.0f / l;

@@ -46,6 +46,8 @@ constexpr int kStatFloats = 4 * 128;   // H * roundup4(F) <= 512 floats per edge
 struct NodeSlot {
   int node, e_begin, e_end;
 };
+struct TrueTag { static constexpr bool value = true; };
+struct FalseTag { static constexpr bool value = false; };
 
 template <int MODE>
 struct BwdSmem {
@@ -317,14 +319,24 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
     constexpr int HQ = HD / 4;                      // P K / dQ columns per head owned by this thread (MODE_DQ)
     constexpr int DEFER = 2;                        // MODE_DQ: items between publishing P and folding delta o (P K)
     uint32_t qi = 0, k = 0, ei = 0, item = 0;
-    const bool do_prof = PROF && blockIdx.x == 0 && warp == 0;
-    long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long tp = do_prof ? clock64() : 0;
-#define AMP_PHASE(i) do { if (do_prof) { const long long now_ = clock64(); pt[i] += now_ - tp; tp = now_; } } while (0)
+    // light-weight wait accounting (debug entry point only): cycles this warp spent blocked on each kind of barrier
+    const bool do_prof = PROF && blockIdx.x == 0 && (warp == 0 || warp == 8);
+    uint32_t wt[6] = {0, 0, 0, 0, 0, 0};
+    const uint32_t t_begin = do_prof ? (uint32_t)clock() : 0u;
+#define AMP_PHASE(i)
+#define AMP_TWAIT(i, bar, parity, code)                                       \
+  do {                                                                        \
+    if (PROF) {                                                               \
+      const uint32_t t0_ = (uint32_t)clock();                                 \
+      AMP_WAIT(bar, parity, code);                                            \
+      wt[i] += (uint32_t)clock() - t0_;                                       \
+    } else {                                                                  \
+      AMP_WAIT(bar, parity, code);                                            \
+    }                                                                         \
+  } while (0)
     for (;;) {
       const uint32_t qb = qi & 1;
-      AMP_WAIT(&sm.own_full[qb], (qi >> 1) & 1, 301);
-      AMP_PHASE(6);
+      AMP_TWAIT(0, &sm.own_full[qb], (qi >> 1) & 1, 301);
       const NodeSlot ns = sm.slot[qb];
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.own_empty[qb]);
@@ -338,8 +350,11 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       // MODE_DQ: folds item `it` (head hp, the t-th... of this node at edge slot ep) into racc and frees its ring slot
       auto fold = [&](uint32_t it, int hp, int ep) -> bool {
         const uint32_t slot = it % R;
+        const uint32_t tf0 = PROF ? (uint32_t)clock() : 0u;
         if (!mbar_wait(&sm.dl_bar[it & 3][q4], (it >> 2) & 1)) return false;
+        const uint32_t tf1 = PROF ? (uint32_t)clock() : 0u;
         if (!mbar_wait(&sm.ko_full[slot], (it / R) & 1)) return false;
+        if (PROF) { wt[4] += tf1 - tf0; wt[5] += (uint32_t)clock() - tf1; }
         tc_fence_after();
         uint32_t ko[HQ];
         if constexpr (HQ == 4) tmem_ld_32x32b_x4(lane_base + kAccCol + 64 + slot * HD + HQ * j4, ko);
@@ -351,35 +366,39 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.ko_empty[slot]);
         if (j4 == 0 && row_ok) delta[((int64_t)ep * H + hp) * Fs + row] = dsum;
+        // hp is a run-time value (rolled head loop): select the accumulator row with predicated updates
 #pragma unroll
-        for (int x = 0; x < HQ; ++x) racc[hp][x] -= dsum * __uint_as_float(ko[x]);
+        for (int hh = 0; hh < H; ++hh) {
+          const float dsel = hh == hp ? dsum : 0.f;
+#pragma unroll
+          for (int x = 0; x < HQ; ++x) racc[hh][x] -= dsel * __uint_as_float(ko[x]);
+        }
         return true;
       };
       for (int e = ns.e_begin; e < ns.e_end; ++e, ++ei) {
         const uint32_t st = ei % NS;
-        if (MODE == MODE_DKV) AMP_WAIT(&sm.edge_full[st], (ei / NS) & 1, 306);   // acquire the bulk-copied statistics rows
-#pragma unroll
+        if (MODE == MODE_DKV) AMP_TWAIT(1, &sm.edge_full[st], (ei / NS) & 1, 306);   // acquire the bulk-copied statistics rows
+        // NOT unrolled: one copy of the body keeps the elementwise loop inside the instruction cache
+#pragma unroll 1
         for (int h = 0; h < H; ++h, ++item, ++t) {
           float L = 0.f;
           if (MODE == MODE_DQ) {
             L = row_ok ? lse2[((int64_t)e * H + h) * Fs + row] : 0.f;
             if (t >= DEFER) {
               // item - DEFER belongs to this node: head (h - DEFER) mod H, edge slot e or e - 1
-              constexpr int dh = DEFER % H;
-              const int hp = (h + H - dh) % H;
+              const int hp = (h + H - DEFER % H) % H;
               const int ep = e - (DEFER + H - 1 - h) / H;
               if (!fold(item - DEFER, hp, ep)) AMP_FAIL(308);
             }
           }
-          const float* Ls = sm.stat[MODE == MODE_DKV ? st : 0][0] + h * Fs;
-          const float* Ds = sm.stat[MODE == MODE_DKV ? st : 0][1] + h * Fs;
-          float dl = 0.f;
+          const uint32_t ls_addr = smem_u32(sm.stat[MODE == MODE_DKV ? st : 0][0] + h * Fs);
+          const uint32_t ds_addr = smem_u32(sm.stat[MODE == MODE_DKV ? st : 0][1] + h * Fs);
+          float2 dl2 = make_float2(0.f, 0.f);
           AMP_PHASE(5);
           for (int half = 0; half < nhalf; ++half, ++k) {
             if ((k & 1) != grp) continue;
             const uint32_t set = k % kSets;
-            AMP_WAIT(&sm.xy_full[set], (k / kSets) & 1, 302);
-            AMP_PHASE(0);
+            AMP_TWAIT(2, &sm.xy_full[set], (k / kSets) & 1, 302);
             tc_fence_after();
             const uint32_t xbase = lane_base + set * 128 + 32 * cb;
             uint32_t xs[2][16], ys[2][16];
@@ -387,35 +406,52 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
             tmem_ld_32x32b_x16(xbase + 64, ys[0]);
             tmem_ld_32x32b_x16(xbase + 16, xs[1]);
             tmem_ld_32x32b_x16(xbase + 64 + 16, ys[1]);
-            tmem_ld_wait();
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
-              uint32_t px[8], py[8];
               const int col0 = 64 * half + 32 * cb + 16 * ch;     // first score column of this chunk
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
+              uint32_t px[8], py[8];
+              if (ch == 0) tmem_ld_wait();
+              // one pair of score columns; TAIL adds the selects that keep columns >= F (zero-filled tile rows, undefined
+              // statistics) out of delta and out of the MMA operands
+              auto pair = [&](int j, float2 l2, float2 d2, auto tail_tag) {
+                constexpr bool TAIL = decltype(tail_tag)::value;
                 const int c0 = col0 + 2 * j;
-                float p0, p1, u0, u1;
+                const float2 x2 = make_float2(__uint_as_float(xs[ch][2 * j]), __uint_as_float(xs[ch][2 * j + 1]));
+                const float2 y2 = make_float2(__uint_as_float(ys[ch][2 * j]), __uint_as_float(ys[ch][2 * j + 1]));
+                float2 p2, u2;
                 if (MODE == MODE_DQ) {
-                  p0 = ex2_approx(__uint_as_float(xs[ch][2 * j]) - L);
-                  p1 = ex2_approx(__uint_as_float(xs[ch][2 * j + 1]) - L);
-                  u0 = p0 * __uint_as_float(ys[ch][2 * j]);
-                  u1 = p1 * __uint_as_float(ys[ch][2 * j + 1]);
+                  const float2 e2 = f2add(x2, make_float2(-L, -L));
+                  p2 = make_float2(ex2_approx(e2.x), ex2_approx(e2.y));
+                  u2 = f2mul(p2, y2);
                 } else {
-                  const float2 l2 = *reinterpret_cast<const float2*>(Ls + c0);
-                  const float2 d2 = *reinterpret_cast<const float2*>(Ds + c0);
-                  p0 = ex2_approx(__uint_as_float(xs[ch][2 * j]) - l2.x);
-                  p1 = ex2_approx(__uint_as_float(xs[ch][2 * j + 1]) - l2.y);
-                  u0 = p0 * (__uint_as_float(ys[ch][2 * j]) - d2.x);
-                  u1 = p1 * (__uint_as_float(ys[ch][2 * j + 1]) - d2.y);
+                  const float2 e2 = f2add(x2, make_float2(-l2.x, -l2.y));
+                  p2 = make_float2(ex2_approx(e2.x), ex2_approx(e2.y));
+                  u2 = f2mul(p2, f2add(y2, make_float2(-d2.x, -d2.y)));
                 }
-                if (F < 128) {
-                  if (c0 >= F) { p0 = 0.f; u0 = 0.f; }
-                  if (c0 + 1 >= F) { p1 = 0.f; u1 = 0.f; }
+                if (TAIL) {
+                  if (c0 >= F) { p2.x = 0.f; u2.x = 0.f; }
+                  if (c0 + 1 >= F) { p2.y = 0.f; u2.y = 0.f; }
                 }
-                dl += u0 + u1;
-                px[j] = pack_bf16x2(p0, p1);
-                py[j] = pack_bf16x2(u0, u1);
+                if (MODE == MODE_DQ) dl2 = f2add(dl2, u2);
+                px[j] = pack_bf16x2(p2.x, p2.y);
+                py[j] = pack_bf16x2(u2.x, u2.y);
+              };
+              // four pairs of column statistics per shared-memory vector load (MODE_DKV)
+              auto quad = [&](int v4, auto tail_tag) {
+                float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a4;
+                if (MODE == MODE_DKV) {
+                  a4 = lds_f4(ls_addr + (col0 + 4 * v4) * 4);
+                  b4 = lds_f4(ds_addr + (col0 + 4 * v4) * 4);
+                }
+                pair(2 * v4, make_float2(a4.x, a4.y), make_float2(b4.x, b4.y), tail_tag);
+                pair(2 * v4 + 1, make_float2(a4.z, a4.w), make_float2(b4.z, b4.w), tail_tag);
+              };
+              if (col0 + 16 > F) {     // warp-uniform: only the chunk that straddles F and the ones behind it
+#pragma unroll
+                for (int v4 = 0; v4 < 4; ++v4) quad(v4, TrueTag{});
+              } else {
+#pragma unroll
+                for (int v4 = 0; v4 < 4; ++v4) quad(v4, FalseTag{});
               }
               // packed operands go to the first 8 of the chunk's own 16 columns: always behind this thread's own reads
               tmem_st_32x32b_x8(xbase + 16 * ch, px);
@@ -430,7 +466,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
           }
           if (MODE == MODE_DQ) {
             // partial delta of this warp's columns (zero when the item had no half-item for this group)
-            sm.dl[item & 3][j4][row] = dl;
+            sm.dl[item & 3][j4][row] = dl2.x + dl2.y;
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.dl_bar[item & 3][q4]);
             AMP_PHASE(3);
@@ -454,8 +490,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
         AMP_PHASE(4);
       }
       // node epilogue: all consumer MMAs of the node have landed in the accumulators
-      AMP_WAIT(&sm.acc_full, qi & 1, 304);
-      AMP_PHASE(6);
+      AMP_TWAIT(3, &sm.acc_full, qi & 1, 304);
       tc_fence_after();
       if (MODE == MODE_DQ) {
         // dQ = TMEM accumulator (sum_e W_e K) + racc; this thread owns columns [h HD + HQ j4, + HQ) of every head
@@ -505,10 +540,13 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       ++qi;
     }
     if (do_prof && lane == 0) {
-      for (int i = 0; i < 8; ++i) prof[i] = pt[i];
-      prof[8] = item;
+      long long* pr = prof + (warp == 0 ? 0 : 16);
+      for (int i = 0; i < 6; ++i) pr[i] = wt[i];
+      pr[6] = (uint32_t)clock() - t_begin;
+      pr[8] = item;
     }
 #undef AMP_PHASE
+#undef AMP_TWAIT
   }
 fail:
   tc_fence_before();

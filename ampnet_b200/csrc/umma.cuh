@@ -312,6 +312,16 @@ __device__ __forceinline__ uint32_t ex2_bf16x2(uint32_t x) {
   return y;
 }
 
+// Packed fp32 pairs (FADD2 / FMUL2 / FFMA2 on sm_100): same lane throughput as the scalar forms, half the issue slots.
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float4 lds_f4(uint32_t smem_addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_addr));
+  return v;
+}
+
 // byte offset inside a 128B-swizzled tile whose rows are 128 bytes and whose base is 1024B aligned
 __host__ __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t byte_in_row) {
   return row * 128u + ((((byte_in_row >> 4) ^ (row & 7u)) << 4) | (byte_in_row & 15u));

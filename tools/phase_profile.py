@@ -56,8 +56,7 @@ def bwd():
     _lib.call("ampconv_attn_fwd_bf16", q, k, v, g.dst_rowptr, g.dst_src, g.inv_deg, None, agg, lse2, *tail)
     prof = torch.zeros(64, dtype=torch.int64, device=dev)
     lib = _lib.load()
-    names = ["wait X/Y", "compute (ld, exp, pack, st)", "publish", "delta exchange", "scale P + publish", "lse load", "node / accumulator wait",
-             "node epilogue"]
+    names = ["own tiles", "edge tiles + statistics", "scores X/Y", "accumulators (node end)", "delta partials", "P K ring"]
     for mode in ("dq", "dkv"):
         prof.zero_()
         lib.ampconv_debug_set_bwd_profile(ctypes.c_void_p(prof.data_ptr()))
@@ -68,22 +67,11 @@ def bwd():
         torch.cuda.synchronize()
         lib.ampconv_debug_set_bwd_profile(ctypes.c_void_p(0))
         p = prof.cpu().tolist()
-        items = max(1, p[8])
-        tot = sum(p[:8])
-        print(f"bwd {mode}: items={items} total cycles/item={tot / items:.0f}")
-        for nm, cyc in zip(names, p[:8]):
-            print(f"  {nm:28s} {cyc / items:8.1f} cyc/item  {100.0 * cyc / tot:5.1f}%")
-        if p[24] > 0:
-            it2 = p[24]
-            print("  last elementwise warp: " + ", ".join(f"{nm} {cyc / it2:.0f}" for nm, cyc in zip(names, p[16:24])))
-        if p[36] > 0:
-            it3 = p[36]
-            print(f"  score-MMA warp /item: wait edge tiles {p[32] / it3:.0f}, wait set free {p[33] / it3:.0f}, "
-                  f"issue+commit {p[34] / it3:.0f}, node wait {p[35] / it3:.0f}")
-        if p[44] > 0:
-            it4 = p[44]
-            print(f"  T-MMA warp 0 /item: wait operands {p[40] / it4:.0f}, issue+commit {p[41] / it4:.0f}, "
-                  f"until T complete {p[42] / it4:.0f}, other {p[43] / it4:.0f}")
+        for off, who in ((0, "elementwise warp 0 (group 0)"), (16, "elementwise warp 8 (group 1)")):
+            items = max(1, p[off + 8])
+            print(f"bwd {mode} {who}: items={items} total cycles/item={p[off + 6] / items:.0f}; blocked per item on: " +
+                  ", ".join(f"{nm} {p[off + i] / items:.0f}" for i, nm in enumerate(names)) +
+                  f"; busy {(p[off + 6] - sum(p[off:off + 6])) / items:.0f}")
 
 
 if __name__ == "__main__":
