@@ -55,12 +55,12 @@ struct BwdSmem {
   uint8_t own[2][2][kTileBytes];        // [slot][tile 0/1]
   uint8_t edge[NS][2][kTileBytes];      // [stage][tile 0/1]
   float stat[MODE == MODE_DKV ? NS : 1][2][kStatFloats];   // MODE_DKV: lse2 / delta rows of the edge
-  float dl[4][4][128];                  // MODE_DQ: partial delta of [item & 3][group * 2 + column block][row]
+  float dl[8][4][128];                  // MODE_DQ: partial delta of [item & 7][group * 2 + column block][row]
   uint64_t own_full[2], own_empty[2];
   uint64_t edge_full[NS], edge_empty[NS];
   uint64_t xy_full[kSets], set_empty[kSets], op_full[kSets];
   uint64_t acc_full, acc_empty;
-  uint64_t dl_bar[4][4];                // MODE_DQ: [item & 3][lane quarter]: the quarter's four warps wrote their partial deltas
+  uint64_t dl_bar[8][4];                // MODE_DQ: [item & 7][lane quarter]: the quarter's four warps wrote their partial deltas
   uint64_t ko_full[4], ko_empty[4];     // MODE_DQ: ring of P K results (slot = item % (64 / HD))
   NodeSlot slot[2];
   uint32_t tmem_base;
@@ -118,7 +118,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       mbar_init(&sm.edge_full[i], 1);
       mbar_init(&sm.edge_empty[i], MODE == MODE_DKV ? 3 + kEwWarps : 3);
     }
-    for (int i = 0; i < 16; ++i) mbar_init(&sm.dl_bar[i >> 2][i & 3], 4);
+    for (int i = 0; i < 32; ++i) mbar_init(&sm.dl_bar[i >> 2][i & 3], 4);
     for (int i = 0; i < 4; ++i) {
       mbar_init(&sm.ko_full[i], 1);
       mbar_init(&sm.ko_empty[i], kEwWarps);
@@ -140,8 +140,10 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
   const int nhalf = F > 64 ? 2 : 1;                  // halves with at least one valid score column
   const uint32_t stat_bytes = (uint32_t)(H * Fs * sizeof(float));
 
+  // register re-partitioning: the four single-lane control warps give registers to the 16 elementwise warps
   if (warp == kEwWarps) {
     // ------------------------------------------------------------------ producer / scheduler
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     uint32_t qi = 0, ei = 0;
     for (;;) {
       int node = -1, eb = 0, ee = 0;
@@ -214,6 +216,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
     }
   } else if (warp == W_SCORE) {
     // ------------------------------------------------------------------ score MMAs X, Y of every half-item
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     {
       const uint32_t idesc_xy = idesc_bf16(128, 64, 0, 0);
       uint32_t qi = 0, edge = 0, k = 0;
@@ -257,6 +260,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
     //   B = an edge tile as MN-major operand: K / K (MODE_DQ), dO / Q' (MODE_DKV)
     //   destination: MODE_DKV block `which` of the node accumulators; MODE_DQ which = 1 the dQ accumulator,
     //   which = 0 the P K ring slot of the item (fresh per item, folded by the elementwise warps).
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     {
       const uint32_t which = warp == W_TY ? 1u : 0u;
       const uint32_t idesc_t = idesc_bf16(128, 16, 0, 1);      // N = 16 per MMA (two per K step when hd = 32)
@@ -308,6 +312,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
     }
   } else {
     // ------------------------------------------------------------------ elementwise warps
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     const uint32_t q4 = warp & 3;                   // TMEM lane quarter
     const uint32_t grp = warp >> 3;                 // group: works on half-items with k & 1 == grp
     const uint32_t cb = (warp >> 2) & 1;            // column block: score columns [32cb, 32cb+32) of the half
@@ -317,7 +322,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
     const uint32_t lane_base = tmem + ((uint32_t)(q4 * 32) << 16);
     constexpr int R = 64 / HD;                      // P K ring slots (MODE_DQ)
     constexpr int HQ = HD / 4;                      // P K / dQ columns per head owned by this thread (MODE_DQ)
-    constexpr int DEFER = 2;                        // MODE_DQ: items between publishing P and folding delta o (P K)
+    constexpr int DEFER = R - 1;                    // MODE_DQ: items between publishing P and folding delta o (P K)
     uint32_t qi = 0, k = 0, ei = 0, item = 0;
     // light-weight wait accounting (debug entry point only): cycles this warp spent blocked on each kind of barrier
     const bool do_prof = PROF && blockIdx.x == 0 && (warp == 0 || warp == 8);
@@ -347,11 +352,12 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
 #pragma unroll
         for (int x = 0; x < HQ; ++x) racc[h][x] = 0.f;
       uint32_t t = 0;                                // items of this node processed so far
+      float L_next = 0.f;
       // MODE_DQ: folds item `it` (head hp, the t-th... of this node at edge slot ep) into racc and frees its ring slot
       auto fold = [&](uint32_t it, int hp, int ep) -> bool {
         const uint32_t slot = it % R;
         const uint32_t tf0 = PROF ? (uint32_t)clock() : 0u;
-        if (!mbar_wait(&sm.dl_bar[it & 3][q4], (it >> 2) & 1)) return false;
+        if (!mbar_wait(&sm.dl_bar[it & 7][q4], (it >> 3) & 1)) return false;
         const uint32_t tf1 = PROF ? (uint32_t)clock() : 0u;
         if (!mbar_wait(&sm.ko_full[slot], (it / R) & 1)) return false;
         if (PROF) { wt[4] += tf1 - tf0; wt[5] += (uint32_t)clock() - tf1; }
@@ -359,7 +365,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
         uint32_t ko[HQ];
         if constexpr (HQ == 4) tmem_ld_32x32b_x4(lane_base + kAccCol + 64 + slot * HD + HQ * j4, ko);
         else tmem_ld_32x32b_x8(lane_base + kAccCol + 64 + slot * HD + HQ * j4, ko);
-        const float* dls = &sm.dl[it & 3][0][row];
+        const float* dls = &sm.dl[it & 7][0][row];
         const float dsum = (dls[0] + dls[128]) + (dls[256] + dls[384]);
         tmem_ld_wait();
         tc_fence_before();
@@ -382,15 +388,22 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
 #pragma unroll 1
         for (int h = 0; h < H; ++h, ++item, ++t) {
           float L = 0.f;
+          bool folded = true;
           if (MODE == MODE_DQ) {
-            L = row_ok ? lse2[((int64_t)e * H + h) * Fs + row] : 0.f;
-            if (t >= DEFER) {
-              // item - DEFER belongs to this node: head (h - DEFER) mod H, edge slot e or e - 1
-              const int hp = (h + H - DEFER % H) % H;
-              const int ep = e - (DEFER + H - 1 - h) / H;
-              if (!fold(item - DEFER, hp, ep)) AMP_FAIL(308);
-            }
+            // the row statistic of the next item of the node is fetched one item ahead (global-load latency off the path)
+            L = t == 0 ? (row_ok ? lse2[((int64_t)e * H + h) * Fs + row] : 0.f) : L_next;
+            const bool last = e + 1 == ns.e_end && h == H - 1;
+            L_next = (!last && row_ok) ? lse2[((int64_t)e * H + h + 1) * Fs + row] : 0.f;
+            folded = t < DEFER;
           }
+          // MODE_DQ: fold item - DEFER (same node: head (h - DEFER) mod H, an earlier edge slot when DEFER > h)
+          auto fold_now = [&]() -> bool {
+            const int hp = (h + H * DEFER - DEFER) % H;
+            const int ep = e - (DEFER + H - 1 - h) / H;
+            folded = true;
+            return fold(item - DEFER, hp, ep);
+          };
+          if (MODE == MODE_DQ && !folded) { if (!fold_now()) AMP_FAIL(308); }
           const uint32_t ls_addr = smem_u32(sm.stat[MODE == MODE_DKV ? st : 0][0] + h * Fs);
           const uint32_t ds_addr = smem_u32(sm.stat[MODE == MODE_DKV ? st : 0][1] + h * Fs);
           float2 dl2 = make_float2(0.f, 0.f);
@@ -466,9 +479,9 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
           }
           if (MODE == MODE_DQ) {
             // partial delta of this warp's columns (zero when the item had no half-item for this group)
-            sm.dl[item & 3][j4][row] = dl2.x + dl2.y;
+            sm.dl[item & 7][j4][row] = dl2.x + dl2.y;
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.dl_bar[item & 3][q4]);
+            if (lane == 0) mbar_arrive(&sm.dl_bar[item & 7][q4]);
             AMP_PHASE(3);
           }
         }
