@@ -6,10 +6,12 @@ problem and the aggregation is a sum per destination, so the path shards by dest
 
 * destinations are range-partitioned into ``world`` contiguous ranges balanced by in-edge count;
   rank r owns the rows of x / Q / out / dX of its range and projects K, V for its own nodes;
-* exchange step, forward: all-gather of the projected K and V (bf16) -- every rank then holds the
-  ``world * max_n`` padded rows its in-edges may reference (source ids are remapped to padded ids once);
-* exchange step, backward: each rank computes the partial dK | dV its local edges contribute to every source
-  and the partials are reduce-scattered to the owners; dQ never leaves the rank;
+* exchange step, forward: a HALO exchange of the projected K and V (bf16) -- every rank receives exactly the
+  remote source rows its in-edges reference (``all_to_all_single`` with per-owner counts; the index lists are
+  exchanged once per graph) and addresses them by compact id: own rows first, halo rows behind them;
+* exchange step, backward: each rank computes the partial dK | dV its local edges contribute to every source it
+  references; the halo rows travel back to their owners (bf16 by default) and are added there in a fixed order
+  (deterministic); dQ never leaves the rank;
 * the four parameter gradients are all-reduced.
 
 Host logic only: the kernels are the ``*_part`` entry points of include/ampconv.h.  The collectives go through
@@ -41,14 +43,10 @@ def partition_ranges(in_degree, world):
     return torch.tensor(bounds, dtype=torch.int64)
 
 
-def padded_id(node, bounds, max_n):
-    """Row of a global node id inside the all-gathered [world * max_n, ...] tensors."""
-    owner = torch.searchsorted(bounds.to(node.device), node, right=True) - 1
-    return owner * max_n + (node - bounds.to(node.device)[owner])
-
-
 class PartitionedGraph:
-    """Local view of rank ``rank``: edges whose destination it owns, destinations as local ids, sources as padded ids."""
+    """Local view of rank ``rank``: the edges whose destination it owns, destinations as local ids, sources as
+    compact ids (``[0, n_local)`` = own nodes, ``n_local + j`` = j-th halo node; halo nodes are sorted by global id,
+    hence grouped by owner)."""
 
     def __init__(self, edge_index, num_nodes, world, rank, bounds=None):
         src, dst = edge_index[0], edge_index[1]
@@ -58,12 +56,42 @@ class PartitionedGraph:
         self.world, self.rank, self.num_nodes = world, rank, int(num_nodes)
         self.lo, self.hi = int(bounds[rank]), int(bounds[rank + 1])
         self.n_local = self.hi - self.lo
-        self.max_n = int((bounds[1:] - bounds[:-1]).max())
         mine = (dst >= self.lo) & (dst < self.hi)
         self.edge_ids = torch.nonzero(mine, as_tuple=False).squeeze(1)       # columns of the global edge_index
-        self.local_edge_index = torch.stack([padded_id(src[mine], bounds, self.max_n), dst[mine] - self.lo]).contiguous()
-        self.num_kv_nodes = world * self.max_n
-        self.graph = None                                                   # device CSR, built lazily
+        s = src[mine]
+        own = (s >= self.lo) & (s < self.hi)
+        self.halo_ids = torch.unique(s[~own])                                # sorted global ids of the remote sources
+        self.n_halo = int(self.halo_ids.numel())
+        halo_pos = torch.searchsorted(self.halo_ids, s) if self.n_halo > 0 else torch.zeros_like(s)
+        compact = torch.where(own, s - self.lo, self.n_local + halo_pos)
+        self.local_edge_index = torch.stack([compact, dst[mine] - self.lo]).contiguous()
+        self.num_kv_nodes = self.n_local + self.n_halo
+        owner = torch.searchsorted(bounds.to(self.halo_ids.device), self.halo_ids, right=True) - 1
+        self.recv_counts = torch.bincount(owner, minlength=world).cpu().tolist()   # halo rows per owner (0 for this rank)
+        self.send_counts = None     # rows this rank sends to every other rank       } filled by build_plan()
+        self.send_idx = None        # local node ids of those rows, grouped by receiver }
+        self.graph = None           # device CSR, built lazily
+
+    def global_id(self, compact):
+        """Global node id of a compact source id."""
+        compact = compact.to(self.halo_ids.device)
+        halo = self.halo_ids[(compact - self.n_local).clamp_min(0)] if self.n_halo > 0 else compact
+        return torch.where(compact < self.n_local, compact + self.lo, halo)
+
+    def build_plan(self, group=None):
+        """One-time exchange of the halo index lists: afterwards every rank knows which of its rows each peer needs."""
+        if self.send_counts is not None:
+            return self
+        dev = self.halo_ids.device
+        recv = torch.tensor(self.recv_counts, dtype=torch.int64, device=dev)
+        send = torch.empty_like(recv)
+        dist.all_to_all_single(send, recv, group=group)
+        self.send_counts = send.cpu().tolist()
+        want = torch.empty(int(sum(self.send_counts)), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(want, self.halo_ids.contiguous(), output_split_sizes=self.send_counts,
+                               input_split_sizes=self.recv_counts, group=group)
+        self.send_idx = (want - self.lo).contiguous()
+        return self
 
     def device_graph(self):
         if self.graph is None:
@@ -102,50 +130,55 @@ class BipartiteGraph:
 
 
 # ------------------------------------------------------------------------------------------ collectives (NCCL or gloo)
-def all_gather_rows(local_padded, world, group=None):
-    """[max_rows, C] per rank -> [world * max_rows, C] (rank-major), same on every rank."""
-    out = local_padded.new_empty((world * local_padded.shape[0],) + tuple(local_padded.shape[1:]))
-    if dist.get_backend(group) == "gloo":
-        parts = list(out.chunk(world, dim=0))
-        dist.all_gather(parts, local_padded.contiguous(), group=group)
-    else:
-        dist.all_gather_into_tensor(out, local_padded.contiguous(), group=group)
-    return out
+def halo_gather(local_rows, halo_out, pg, group=None):
+    """Forward exchange: local_rows [n_local, C] -> halo_out [n_halo, C], the rows of the remote sources this rank's
+    edges reference (row j = node pg.halo_ids[j]).  Requires pg.build_plan()."""
+    send = local_rows.index_select(0, pg.send_idx)
+    dist.all_to_all_single(halo_out, send, output_split_sizes=pg.recv_counts, input_split_sizes=pg.send_counts, group=group)
+    return halo_out
 
 
-def reduce_scatter_rows(partial, world, rank, group=None):
-    """[world * max_rows, C] partial sums per rank -> [max_rows, C]: the sum over ranks of this rank's chunk."""
-    rows = partial.shape[0] // world
-    if dist.get_backend(group) == "gloo":
-        full = partial.clone()
-        dist.all_reduce(full, group=group)
-        return full[rank * rows:(rank + 1) * rows].contiguous()
-    out = partial.new_empty((rows,) + tuple(partial.shape[1:]))
-    dist.reduce_scatter_tensor(out, partial.contiguous(), group=group)
-    return out
+def halo_scatter_add(halo_rows, local_acc, pg, group=None):
+    """Backward exchange: halo_rows [n_halo, C] (partial sums for remote sources) travel to their owners and are added
+    into local_acc [n_local, C] (fp32), one sender block after the other (unique ids per block: deterministic)."""
+    recv = halo_rows.new_empty((int(sum(pg.send_counts)),) + tuple(halo_rows.shape[1:]))
+    dist.all_to_all_single(recv, halo_rows.contiguous(), output_split_sizes=pg.send_counts, input_split_sizes=pg.recv_counts,
+                           group=group)
+    o = 0
+    for cnt in pg.send_counts:
+        if cnt:
+            local_acc.index_add_(0, pg.send_idx[o:o + cnt], recv[o:o + cnt].to(local_acc.dtype))
+        o += cnt
+    return local_acc
 
 
 # ------------------------------------------------------------------------------------------ the layer
+GRAD_EXCHANGE_DTYPE = torch.bfloat16   # dtype of the dK | dV halo rows on the wire (torch.float32: exact partial sums)
+
+
 class _DistAMPConvFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_local, w_in, b_in, w_out, b_out, pg, num_heads, group):
         dev = x_local.device
         g = pg.device_graph()
+        pg.build_plan(group)
         n, width = x_local.shape
         d = w_in.shape[1]
         f = width // d
         hd = d // num_heads
-        world, max_n = pg.world, pg.max_n
-        rows, prow = n * f, max_n * f
+        rows, krows = n * f, pg.num_kv_nodes * f
         with torch.cuda.device(dev):
             st = F_._stream(dev)
             ws = torch.zeros(64, dtype=torch.int32, device=dev)
             q = torch.empty((rows, d), dtype=torch.bfloat16, device=dev)
-            kv_local = torch.zeros((2, prow, d), dtype=torch.bfloat16, device=dev)    # padded rows stay zero
-            _lib.call("ampconv_qkv_proj_tc", x_local, w_in, b_in, q, kv_local[0], kv_local[1], _lib.i64(rows), _lib.i32(d),
+            # K, V of own nodes first, halo rows behind them (compact ids of pg.local_edge_index)
+            k_all = torch.empty((krows, d), dtype=torch.bfloat16, device=dev)
+            v_all = torch.empty((krows, d), dtype=torch.bfloat16, device=dev)
+            _lib.call("ampconv_qkv_proj_tc", x_local, w_in, b_in, q, k_all, v_all, _lib.i64(rows), _lib.i32(d),
                       _lib.f32(F_.LOG2E / hd ** 0.5), ws, st)
-            k_all = all_gather_rows(kv_local[0], world, group)
-            v_all = all_gather_rows(kv_local[1], world, group)
+            if pg.world > 1:
+                halo_gather(k_all[:rows].view(n, f * d), k_all[rows:].view(pg.n_halo, f * d), pg, group)
+                halo_gather(v_all[:rows].view(n, f * d), v_all[rows:].view(pg.n_halo, f * d), pg, group)
             agg = torch.empty((rows, d), dtype=torch.float32, device=dev)
             lse2 = torch.empty((g.num_edges, num_heads, (f + 3) // 4 * 4), dtype=torch.float32, device=dev)
             out = torch.empty((n, width), dtype=torch.float32, device=dev)
@@ -166,7 +199,7 @@ class _DistAMPConvFunction(torch.autograd.Function):
         n, width = x_local.shape
         d = w_in.shape[1]
         f = width // d
-        rows, prow = n * f, pg.max_n * f
+        rows = n * f
         e = g.num_edges
         with torch.cuda.device(dev):
             st = F_._stream(dev)
@@ -185,12 +218,16 @@ class _DistAMPConvFunction(torch.autograd.Function):
                     _lib.size_t(256), st)
             _lib.call("ampconv_attn_bwd_dq_bf16_part", q, k_all, v_all, d_agg, lse2, g.dst_rowptr, g.dst_src, g.order_dst, d_q, delta,
                       *tail)
+            # partial dK | dV of the local edges for every referenced source: own rows first, halo rows behind them
             d_kv_partial = torch.empty((pg.num_kv_nodes * f, 2 * d), dtype=torch.float32, device=dev)
             _lib.call("ampconv_attn_bwd_dkv_bf16_part", q, k_all, v_all, d_agg, lse2, delta, g.src_rowptr, g.src_dst,
                       g.src_pos, g.order_src, d_kv_partial, *tail)
-            d_kv = reduce_scatter_rows(d_kv_partial, pg.world, pg.rank, group)        # [max_n * F, 2d], rows >= n*F are padding
+            d_kv = d_kv_partial[:rows]
+            if pg.world > 1:
+                halo = d_kv_partial[rows:].view(pg.n_halo, f * 2 * d).to(GRAD_EXCHANGE_DTYPE)
+                halo_scatter_add(halo, d_kv.view(n, f * 2 * d), pg, group)
+            d_qkv = torch.cat([d_q, d_kv], dim=1)
             del d_kv_partial
-            d_qkv = torch.cat([d_q, d_kv[:rows]], dim=1)
             d_x = torch.empty_like(x_local)
             d_w_in = torch.empty_like(w_in)
             d_b_in = torch.empty(3 * d, dtype=torch.float32, device=dev)
@@ -198,7 +235,8 @@ class _DistAMPConvFunction(torch.autograd.Function):
             _lib.call("ampconv_qkv_proj_bwd_params_tc", x_local, d_qkv, d_w_in, d_b_in, _lib.i64(rows), _lib.i32(d), ws,
                       _lib.size_t(ws.numel()), bws, st)
             flat = torch.cat([d_w_in.flatten(), d_b_in, d_w_out.flatten(), d_b_out])
-            dist.all_reduce(flat, group=group)
+            if pg.world > 1:
+                dist.all_reduce(flat, group=group)
             o = 0
             outs = []
             for t in (d_w_in, d_b_in, d_w_out, d_b_out):

@@ -318,15 +318,16 @@ def run_ours(args):
 
 
 def run_ours_partitioned(args, spec, world, rank, dev):
-    """N > 1: the SAME graph, destination-partitioned over the ranks (strong scaling); K/V all-gather forward,
-    dK/dV reduce-scatter and parameter-gradient all-reduce backward (ampnet_b200/distributed.py)."""
+    """N > 1: the SAME graph, destination-partitioned over the ranks (strong scaling); halo exchange of the referenced
+    K/V rows forward, return of the dK/dV halo rows and parameter-gradient all-reduce backward
+    (ampnet_b200/distributed.py)."""
     import torch.distributed as dist
     from ampnet_b200 import AMPConv, _lib, distributed as D
     n, e, f, d, h = spec["n"], spec["e"], spec["f"], spec["d"], spec["h"]
     edge_index_np = make_problem(spec, args.graph, seed=0)            # identical on every rank
     ei_host = torch.from_numpy(edge_index_np).pin_memory()
     edge_index = ei_host.to(dev)
-    pg = D.PartitionedGraph(edge_index, n, world, rank)
+    pg = D.PartitionedGraph(edge_index, n, world, rank).build_plan()
     pg.device_graph()
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     x = torch.randn((pg.n_local, f * d), generator=gen, device=dev)
@@ -404,7 +405,8 @@ def run_ours_partitioned(args, spec, world, rank, dev):
         "config": {"workload": f"{args.workload}: {spec['desc']} (N={n}, E={e}, F={f}, d={d}, H={h}), one AMPConv layer "
                                f"fwd+bwd, {args.graph} graph seed 7", "mode": "bf16",
                    "l2": "inputs larger than L2; no flush",
-                   "parallelism": f"dst-partitioned over {world} GPUs: all-gather K|V (bf16), reduce-scatter dK|dV (fp32), "
+                   "parallelism": f"dst-partitioned over {world} GPUs: halo exchange of referenced K|V rows (bf16 all-to-all), "
+                                  "dK|dV halo rows back to their owners (bf16 all-to-all, fixed-order adds), "
                                   "all-reduce parameter gradients (NCCL)"},
         "node_updates_per_s": n / (ms_step * 1e-3),
         "clocks": clocks.summary(),

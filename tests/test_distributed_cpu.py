@@ -1,5 +1,5 @@
-"""Host logic of the destination-partitioned (N > 1) path on CPU with gloo, world_size 2: partition balance,
-padded-id remapping, the all-gather layout of K/V and the reduce-scatter of the source-side gradients.
+"""Host logic of the destination-partitioned (N > 1) path on CPU with gloo, world_size 2 and 3: partition balance,
+compact-id remapping, the halo exchange of K/V rows and the return of the source-side gradient rows to their owners.
 The CUDA kernels cannot run here; plain torch index ops stand in for them (this tests the plumbing, not the math)."""
 import os
 import socket
@@ -25,18 +25,22 @@ def test_partition_ranges_balance_in_edges():
         assert float(loads.max()) <= 20000 / world + float(deg.max())
 
 
-def test_local_edges_cover_the_global_edge_set_and_padded_ids_invert():
+def test_local_edges_cover_the_global_edge_set_and_compact_ids_invert():
     n, e, world = 300, 4000, 4
     ei = torch.from_numpy(cases.make_graph("uniform", n, e, seed=9))
     seen = torch.zeros(e, dtype=torch.int64)
     for r in range(world):
         pg = D.PartitionedGraph(ei, n, world, r)
         seen[pg.edge_ids] += 1
-        src_pad, dst_loc = pg.local_edge_index
-        owner = src_pad // pg.max_n
-        assert torch.equal(pg.bounds[owner] + src_pad % pg.max_n, ei[0, pg.edge_ids])
+        src_c, dst_loc = pg.local_edge_index
+        assert torch.equal(pg.global_id(src_c), ei[0, pg.edge_ids])
         assert torch.equal(dst_loc + pg.lo, ei[1, pg.edge_ids])
-        assert int(dst_loc.max()) < pg.n_local
+        assert int(dst_loc.max()) < pg.n_local and int(src_c.max()) < pg.num_kv_nodes
+        # halo = exactly the remote sources of the local edges, grouped by owner, none owned by this rank
+        remote = ei[0, pg.edge_ids]
+        remote = remote[(remote < pg.lo) | (remote >= pg.hi)]
+        assert torch.equal(pg.halo_ids, torch.unique(remote))
+        assert pg.recv_counts[r] == 0 and sum(pg.recv_counts) == pg.n_halo
     assert torch.all(seen == 1)
 
 
@@ -48,15 +52,17 @@ def _worker(rank, world, port, n, e, c, ret):
         g = torch.Generator().manual_seed(0)
         feat = torch.randn(n, c, generator=g)          # stands for the projected K (or V) of every node
         grad_msg = torch.randn(e, c, generator=g)      # stands for the per-edge source-side gradient
-        pg = D.PartitionedGraph(ei, n, world, rank)
-        # forward exchange: pad the local rows, all-gather, look sources up by padded id
-        local = torch.zeros(pg.max_n, c)
-        local[:pg.n_local] = feat[pg.lo:pg.hi]
-        gathered = D.all_gather_rows(local, world)
-        assert torch.equal(gathered[pg.local_edge_index[0]], feat[ei[0, pg.edge_ids]])
-        # backward exchange: partial scatter-add over padded sources, reduce-scatter to the owners
-        partial = torch.zeros(world * pg.max_n, c).index_add_(0, pg.local_edge_index[0], grad_msg[pg.edge_ids])
-        mine = D.reduce_scatter_rows(partial, world, rank)[:pg.n_local]
+        pg = D.PartitionedGraph(ei, n, world, rank).build_plan()
+        assert sum(pg.send_counts) == pg.send_idx.numel() and pg.send_counts[rank] == 0
+        # forward exchange: own rows + halo rows, sources looked up by compact id
+        rows = torch.empty(pg.num_kv_nodes, c)
+        rows[:pg.n_local] = feat[pg.lo:pg.hi]
+        D.halo_gather(rows[:pg.n_local], rows[pg.n_local:], pg)
+        assert torch.equal(rows[pg.local_edge_index[0]], feat[ei[0, pg.edge_ids]])
+        # backward exchange: partial scatter-add over compact sources, halo rows added at their owners
+        partial = torch.zeros(pg.num_kv_nodes, c).index_add_(0, pg.local_edge_index[0], grad_msg[pg.edge_ids])
+        mine = partial[:pg.n_local].clone()
+        D.halo_scatter_add(partial[pg.n_local:], mine, pg)
         ref = torch.zeros(n, c).index_add_(0, ei[0], grad_msg)[pg.lo:pg.hi]
         ret[rank] = float((mine - ref).abs().max())
     finally:
@@ -70,4 +76,14 @@ def test_exchange_steps_world2_gloo():
     world = 2
     ret = mp.Manager().dict()
     mp.spawn(_worker, args=(world, port, 200, 3000, 8, ret), nprocs=world, join=True)
+    assert len(ret) == world and all(v < 1e-4 for v in ret.values()), dict(ret)
+
+
+def test_exchange_steps_world3_gloo():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    world = 3
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, port, 150, 1200, 4, ret), nprocs=world, join=True)
     assert len(ret) == world and all(v < 1e-4 for v in ret.values()), dict(ret)
