@@ -93,7 +93,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
                      const int32_t* __restrict__ slot_of, const int32_t* __restrict__ order,
                      const float* __restrict__ lse2, float* __restrict__ delta, float* __restrict__ d_qkv, int* __restrict__ counter, int* __restrict__ status,
                      int N, int F, float out_scale0, float out_scale1, int out_ld, int out_c0, int out_c1,
-                     long long* __restrict__ prof) {
+                     uint16_t* __restrict__ halo_bf16, int halo_from, long long* __restrict__ prof) {
   using Smem = BwdSmem<MODE>;
   constexpr int NS = Smem::NS;
   constexpr int H = kD / HD;
@@ -159,7 +159,8 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       eb = __shfl_sync(0xffffffffu, eb, 0);
       ee = __shfl_sync(0xffffffffu, ee, 0);
       if (node >= 0 && ee == eb) {
-        // node without edges in this pass: its gradient rows are zero
+        // node without edges in this pass: its gradient rows are zero (halo sources always have an edge)
+        if (halo_bf16 != nullptr && node >= halo_from) continue;
         const int nblk = MODE == MODE_DQ ? 1 : 2;
         for (int i = lane; i < F * nblk * (kD / 4); i += 32) {
           const int r = i / (nblk * (kD / 4)), rem = i - r * (nblk * (kD / 4));
@@ -541,12 +542,24 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
         if (row_ok) {
           const bool is_dv = j4 < 2;
           const float sc = is_dv ? out_scale1 : out_scale0;
-          float4* o = reinterpret_cast<float4*>(d_qkv + ((int64_t)ns.node * F + row) * out_ld +
+          if (halo_bf16 != nullptr && ns.node >= halo_from) {
+            // halo source (multi-GPU): this partial row travels to its owner, written as bf16 [node - halo_from][row][out_ld]
+            uint4* o = reinterpret_cast<uint4*>(halo_bf16 + ((int64_t)(ns.node - halo_from) * F + row) * out_ld +
                                                 (is_dv ? out_c1 : out_c0) + 32 * (j4 & 1));
 #pragma unroll
-          for (int x = 0; x < 32; x += 4)
-            o[x >> 2] = make_float4(__uint_as_float(a[x]) * sc, __uint_as_float(a[x + 1]) * sc,
-                                    __uint_as_float(a[x + 2]) * sc, __uint_as_float(a[x + 3]) * sc);
+            for (int x = 0; x < 32; x += 8)
+              o[x >> 3] = make_uint4(pack_bf16x2(__uint_as_float(a[x]) * sc, __uint_as_float(a[x + 1]) * sc),
+                                     pack_bf16x2(__uint_as_float(a[x + 2]) * sc, __uint_as_float(a[x + 3]) * sc),
+                                     pack_bf16x2(__uint_as_float(a[x + 4]) * sc, __uint_as_float(a[x + 5]) * sc),
+                                     pack_bf16x2(__uint_as_float(a[x + 6]) * sc, __uint_as_float(a[x + 7]) * sc));
+          } else {
+            float4* o = reinterpret_cast<float4*>(d_qkv + ((int64_t)ns.node * F + row) * out_ld +
+                                                  (is_dv ? out_c1 : out_c0) + 32 * (j4 & 1));
+#pragma unroll
+            for (int x = 0; x < 32; x += 4)
+              o[x >> 2] = make_float4(__uint_as_float(a[x]) * sc, __uint_as_float(a[x + 1]) * sc,
+                                      __uint_as_float(a[x + 2]) * sc, __uint_as_float(a[x + 3]) * sc);
+          }
         }
       }
       AMP_PHASE(7);
@@ -573,18 +586,18 @@ template <int HD, int MODE>
 int launch_bwd(const CUtensorMap& own0, const CUtensorMap& own1, const CUtensorMap& oth0, const CUtensorMap& oth1,
                const int32_t* rowptr, const int32_t* nbr, const int32_t* slot_of, const int32_t* order, const float* lse2,
                float* delta, float* d_qkv, int* counter, int* status, int N, int F, float s0, float s1, int out_ld, int out_c0,
-               int out_c1, cudaStream_t stream) {
+               int out_c1, uint16_t* halo_bf16, int halo_from, cudaStream_t stream) {
   const size_t smem = sizeof(BwdSmem<MODE>) + 1024;
   const int grid = N < sm_count() ? N : sm_count();
   long long* prof = g_bwd_prof;
   if (prof) {
     AMPCONV_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_bf16_kernel<HD, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attn_bwd_bf16_kernel<HD, MODE, true><<<grid, kThreads, smem, stream>>>(own0, own1, oth0, oth1, rowptr, nbr, slot_of, order, lse2, delta,
-                                                                          d_qkv, counter, status, N, F, s0, s1, out_ld, out_c0, out_c1, prof);
+                                                                          d_qkv, counter, status, N, F, s0, s1, out_ld, out_c0, out_c1, halo_bf16, halo_from, prof);
   } else {
     AMPCONV_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_bf16_kernel<HD, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attn_bwd_bf16_kernel<HD, MODE, false><<<grid, kThreads, smem, stream>>>(own0, own1, oth0, oth1, rowptr, nbr, slot_of, order, lse2, delta,
-                                                                           d_qkv, counter, status, N, F, s0, s1, out_ld, out_c0, out_c1, nullptr);
+                                                                           d_qkv, counter, status, N, F, s0, s1, out_ld, out_c0, out_c1, halo_bf16, halo_from, nullptr);
   }
   AMPCONV_CHECK_LAUNCH();
   return AMPCONV_OK;
@@ -601,7 +614,8 @@ extern "C" int ampconv_attn_bf16_supported(int F, int d, int H);
 static int bwd_common(int mode, const void* q, const void* k, const void* v, const void* d_agg_bf16,
                       const int32_t* rowptr, const int32_t* nbr, const int32_t* slot_of, const int32_t* order,
                       const float* lse2, float* delta, float* out, int out_ld, int out_c0, int out_c1, int64_t N_dst, int64_t N_kv, int64_t E, int F, int d,
-                      int H, void* workspace, size_t workspace_bytes, void* stream_) {
+                      int H, void* workspace, size_t workspace_bytes, void* stream_, void* halo_bf16 = nullptr,
+                      int64_t halo_from = 0) {
   AMPCONV_REQUIRE(N_dst >= 0 && N_kv >= 0 && E >= 0 && F > 0 && d > 0 && H > 0 && d % H == 0);
   if (!ampconv_attn_bf16_supported(F, d, H)) return AMPCONV_ERR_UNSUPPORTED;
   const int64_t N_own = mode == MODE_DQ ? N_dst : N_kv;
@@ -625,16 +639,16 @@ static int bwd_common(int mode, const void* q, const void* k, const void* v, con
     // dQ = hd^-1/2 * (dS K)
     if (hd == 16)
       return launch_bwd<16, MODE_DQ>(mq, mg, mk, mv, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)N_own, F,
-                                    inv_sqrt_hd, 0.f, out_ld, out_c0, out_c1, stream);
+                                    inv_sqrt_hd, 0.f, out_ld, out_c0, out_c1, nullptr, 0, stream);
     return launch_bwd<32, MODE_DQ>(mq, mg, mk, mv, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)N_own, F,
-                                  inv_sqrt_hd, 0.f, out_ld, out_c0, out_c1, stream);
+                                  inv_sqrt_hd, 0.f, out_ld, out_c0, out_c1, nullptr, 0, stream);
   }
   // dK = hd^-1/2 * dS^T Q = ln2 * dS^T Q'  (Q' = Q * log2e / sqrt(hd)),  dV = P^T dO
   if (hd == 16)
     return launch_bwd<16, MODE_DKV>(mk, mv, mq, mg, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)N_own, F,
-                                   ln2, 1.f, out_ld, out_c0, out_c1, stream);
+                                   ln2, 1.f, out_ld, out_c0, out_c1, reinterpret_cast<uint16_t*>(halo_bf16), (int)halo_from, stream);
   return launch_bwd<32, MODE_DKV>(mk, mv, mq, mg, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)N_own, F, ln2,
-                                 1.f, out_ld, out_c0, out_c1, stream);
+                                 1.f, out_ld, out_c0, out_c1, reinterpret_cast<uint16_t*>(halo_bf16), (int)halo_from, stream);
 }
 
 extern "C" int ampconv_attn_bwd_dq_bf16(const void* q, const void* k, const void* v, const void* d_agg_bf16,
@@ -673,6 +687,20 @@ extern "C" int ampconv_attn_bwd_dkv_bf16_part(const void* q, const void* k, cons
                                               int H, void* workspace, size_t workspace_bytes, void* stream) {
   return bwd_common(MODE_DKV, q, k, v, d_agg_bf16, src_rowptr, src_dst, src_pos, order, lse2, const_cast<float*>(delta), d_kv,
                     2 * kD, 0, kD, num_nodes, num_kv_nodes, E, F, d, H, workspace, workspace_bytes, stream);
+}
+
+// As ampconv_attn_bwd_dkv_bf16_part, for the halo exchange: sources [0, num_own) are this rank's nodes, their rows go to
+// d_kv_own fp32 [num_own*F, 128]; sources [num_own, num_kv_nodes) are halo nodes, their partial rows are written as bf16
+// into d_kv_halo [(num_kv_nodes - num_own)*F, 128], ready to be sent to their owners.
+extern "C" int ampconv_attn_bwd_dkv_bf16_halo(const void* q, const void* k, const void* v, const void* d_agg_bf16,
+                                              const float* lse2, const float* delta, const int32_t* src_rowptr,
+                                              const int32_t* src_dst, const int32_t* src_pos, const int32_t* order,
+                                              float* d_kv_own, void* d_kv_halo, int64_t num_nodes, int64_t num_own,
+                                              int64_t num_kv_nodes, int64_t E, int F, int d, int H, void* workspace,
+                                              size_t workspace_bytes, void* stream) {
+  AMPCONV_REQUIRE(num_own >= 0 && num_own <= num_kv_nodes && (num_own == num_kv_nodes || d_kv_halo != nullptr));
+  return bwd_common(MODE_DKV, q, k, v, d_agg_bf16, src_rowptr, src_dst, src_pos, order, lse2, const_cast<float*>(delta), d_kv_own,
+                    2 * kD, 0, kD, num_nodes, num_kv_nodes, E, F, d, H, workspace, workspace_bytes, stream, d_kv_halo, num_own);
 }
 
 // Debug: when set to a device buffer of 64 int64, the next backward launches run the instrumented kernel and fill it

@@ -1,0 +1,50 @@
+// Multi-GPU halo exchange helpers: the rows that come back from the peers in the backward pass are
+// partial dK | dV sums for this rank's own source nodes.  They are added into the fp32 gradient in a fixed order
+// (sender rank, then position), one thread per output element: deterministic, no atomics.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace ampconv {
+namespace {
+
+// acc[tgt[i], :] += sum_{j in [rowptr[i], rowptr[i+1])} recv[pos[j], :]     (row = row_vec4 * 4 elements)
+__global__ void halo_add_bf16_kernel(const uint2* __restrict__ recv, const int32_t* __restrict__ tgt,
+                                     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ pos,
+                                     float4* __restrict__ acc, int64_t n_tgt, int row_vec4) {
+  const int64_t total = n_tgt * row_vec4;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = idx / row_vec4;
+    const int c = (int)(idx - i * row_vec4);
+    float4* dst = acc + (int64_t)tgt[i] * row_vec4 + c;
+    float4 a = *dst;
+    for (int j = rowptr[i]; j < rowptr[i + 1]; ++j) {
+      const uint2 r = recv[(int64_t)pos[j] * row_vec4 + c];      // four bf16
+      a.x += __uint_as_float(r.x << 16);
+      a.y += __uint_as_float(r.x & 0xFFFF0000u);
+      a.z += __uint_as_float(r.y << 16);
+      a.w += __uint_as_float(r.y & 0xFFFF0000u);
+    }
+    *dst = a;
+  }
+}
+
+}  // namespace
+}  // namespace ampconv
+
+using namespace ampconv;
+
+extern "C" int ampconv_halo_add_bf16(const void* recv_bf16, const int32_t* tgt, const int32_t* rowptr, const int32_t* pos,
+                                     float* acc, int64_t n_tgt, int64_t row_elems, void* stream_) {
+  AMPCONV_REQUIRE(n_tgt >= 0 && row_elems > 0 && row_elems % 4 == 0);
+  if (n_tgt == 0) return AMPCONV_OK;
+  AMPCONV_REQUIRE(recv_bf16 && tgt && rowptr && pos && acc);
+  const int64_t total = n_tgt * (row_elems / 4);
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  halo_add_bf16_kernel<<<(int)blocks, 256, 0, as_stream(stream_)>>>(
+      reinterpret_cast<const uint2*>(recv_bf16), tgt, rowptr, pos, reinterpret_cast<float4*>(acc), n_tgt, (int)(row_elems / 4));
+  AMPCONV_CHECK_LAUNCH();
+  return AMPCONV_OK;
+}

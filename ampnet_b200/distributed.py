@@ -91,6 +91,15 @@ class PartitionedGraph:
         dist.all_to_all_single(want, self.halo_ids.contiguous(), output_split_sizes=self.send_counts,
                                input_split_sizes=self.recv_counts, group=group)
         self.send_idx = (want - self.lo).contiguous()
+        # receive-side plan of the backward exchange: per own node, the positions of its partial rows in the receive
+        # buffer, in sender order (stable sort) -> deterministic accumulation
+        order = torch.sort(self.send_idx, stable=True)
+        self.add_pos = order.indices.to(torch.int32).contiguous()
+        tgt, counts = torch.unique_consecutive(order.values, return_counts=True)
+        self.add_tgt = tgt.to(torch.int32).contiguous()
+        rowptr = torch.zeros(tgt.numel() + 1, dtype=torch.int64, device=dev)
+        rowptr[1:] = torch.cumsum(counts, 0)
+        self.add_rowptr = rowptr.to(torch.int32).contiguous()
         return self
 
     def device_graph(self):
@@ -156,6 +165,43 @@ def halo_scatter_add(halo_rows, local_acc, pg, group=None):
 GRAD_EXCHANGE_DTYPE = torch.bfloat16   # dtype of the dK | dV halo rows on the wire (torch.float32: exact partial sums)
 
 
+class _PhaseTimer:
+    """Optional per-phase device timing of the partitioned step (AMPNET_B200_DIST_TIMING=1): CUDA events on the current
+    stream, summarised by ``phase_summary()``.  Off by default: no events, no synchronisation."""
+
+    def __init__(self):
+        import os
+        self.on = os.environ.get("AMPNET_B200_DIST_TIMING", "0") == "1"
+        self.marks = []
+
+    def mark(self, name):
+        if self.on:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.marks.append((name, ev))
+
+    def summary(self):
+        if not self.marks:
+            return {}
+        torch.cuda.synchronize()
+        acc, cnt = {}, {}
+        for (n0, e0), (n1, e1) in zip(self.marks[:-1], self.marks[1:]):
+            if n1 == "start":
+                continue
+            acc[n1] = acc.get(n1, 0.0) + e0.elapsed_time(e1)
+            cnt[n1] = cnt.get(n1, 0) + 1
+        self.marks = []
+        return {k: acc[k] / cnt[k] for k in acc}
+
+
+TIMER = _PhaseTimer()
+
+
+def phase_summary():
+    """Mean milliseconds per phase since the last call (empty unless AMPNET_B200_DIST_TIMING=1)."""
+    return TIMER.summary()
+
+
 class _DistAMPConvFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_local, w_in, b_in, w_out, b_out, pg, num_heads, group):
@@ -170,22 +216,27 @@ class _DistAMPConvFunction(torch.autograd.Function):
         with torch.cuda.device(dev):
             st = F_._stream(dev)
             ws = torch.zeros(64, dtype=torch.int32, device=dev)
+            TIMER.mark("start")
             q = torch.empty((rows, d), dtype=torch.bfloat16, device=dev)
             # K, V of own nodes first, halo rows behind them (compact ids of pg.local_edge_index)
             k_all = torch.empty((krows, d), dtype=torch.bfloat16, device=dev)
             v_all = torch.empty((krows, d), dtype=torch.bfloat16, device=dev)
             _lib.call("ampconv_qkv_proj_tc", x_local, w_in, b_in, q, k_all, v_all, _lib.i64(rows), _lib.i32(d),
                       _lib.f32(F_.LOG2E / hd ** 0.5), ws, st)
+            TIMER.mark("fwd qkv projection")
             if pg.world > 1:
                 halo_gather(k_all[:rows].view(n, f * d), k_all[rows:].view(pg.n_halo, f * d), pg, group)
                 halo_gather(v_all[:rows].view(n, f * d), v_all[rows:].view(pg.n_halo, f * d), pg, group)
+            TIMER.mark("fwd halo exchange K|V")
             agg = torch.empty((rows, d), dtype=torch.float32, device=dev)
             lse2 = torch.empty((g.num_edges, num_heads, (f + 3) // 4 * 4), dtype=torch.float32, device=dev)
             out = torch.empty((n, width), dtype=torch.float32, device=dev)
             _lib.call("ampconv_attn_fwd_bf16_part", q, k_all, v_all, g.dst_rowptr, g.dst_src, g.inv_deg, g.order_dst, agg, lse2,
                       _lib.i64(n), _lib.i64(pg.num_kv_nodes), _lib.i64(g.num_edges), _lib.i32(f), _lib.i32(d),
                       _lib.i32(num_heads), ws, _lib.size_t(256), st)
+            TIMER.mark("fwd attention")
             _lib.call("ampconv_out_proj_tc", agg, w_out, b_out, g.has_in, out, _lib.i64(n), _lib.i32(f), _lib.i32(d), ws, st)
+            TIMER.mark("fwd out projection")
         ctx.save_for_backward(x_local, w_in, w_out)
         ctx.state = (pg, group, num_heads, q, k_all, v_all, agg, lse2, ws)
         return out
@@ -204,6 +255,7 @@ class _DistAMPConvFunction(torch.autograd.Function):
         with torch.cuda.device(dev):
             st = F_._stream(dev)
             d_out = d_out.contiguous()
+            TIMER.mark("loss (caller)")
             d_agg = torch.empty((rows, d), dtype=torch.bfloat16, device=dev)
             d_w_out = torch.empty_like(w_out)
             d_b_out = torch.empty(d, dtype=torch.float32, device=dev)
@@ -212,31 +264,49 @@ class _DistAMPConvFunction(torch.autograd.Function):
                       bws, st)
             _lib.call("ampconv_out_proj_bwd_params_tc", d_out, agg, g.has_in, d_w_out, d_b_out, _lib.i64(n), _lib.i32(f),
                       _lib.i32(d), ws, _lib.size_t(ws.numel()), bws, st)
+            TIMER.mark("bwd out projection")
             d_q = torch.empty((rows, d), dtype=torch.float32, device=dev)
             delta = torch.empty_like(lse2)
             tail = (_lib.i64(n), _lib.i64(pg.num_kv_nodes), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(h), bws,
                     _lib.size_t(256), st)
             _lib.call("ampconv_attn_bwd_dq_bf16_part", q, k_all, v_all, d_agg, lse2, g.dst_rowptr, g.dst_src, g.order_dst, d_q, delta,
                       *tail)
-            # partial dK | dV of the local edges for every referenced source: own rows first, halo rows behind them
-            d_kv_partial = torch.empty((pg.num_kv_nodes * f, 2 * d), dtype=torch.float32, device=dev)
-            _lib.call("ampconv_attn_bwd_dkv_bf16_part", q, k_all, v_all, d_agg, lse2, delta, g.src_rowptr, g.src_dst,
-                      g.src_pos, g.order_src, d_kv_partial, *tail)
-            d_kv = d_kv_partial[:rows]
-            if pg.world > 1:
-                halo = d_kv_partial[rows:].view(pg.n_halo, f * 2 * d).to(GRAD_EXCHANGE_DTYPE)
-                halo_scatter_add(halo, d_kv.view(n, f * 2 * d), pg, group)
+            TIMER.mark("bwd attention dQ")
+            # partial dK | dV of the local edges for every referenced source: own rows (fp32) and halo rows
+            if pg.world > 1 and GRAD_EXCHANGE_DTYPE == torch.bfloat16:
+                d_kv = torch.empty((rows, 2 * d), dtype=torch.float32, device=dev)
+                halo = torch.empty((pg.n_halo, f * 2 * d), dtype=torch.bfloat16, device=dev)
+                _lib.call("ampconv_attn_bwd_dkv_bf16_halo", q, k_all, v_all, d_agg, lse2, delta, g.src_rowptr, g.src_dst,
+                          g.src_pos, g.order_src, d_kv, halo, _lib.i64(n), _lib.i64(n), _lib.i64(pg.num_kv_nodes), _lib.i64(e),
+                          _lib.i32(f), _lib.i32(d), _lib.i32(h), bws, _lib.size_t(256), st)
+                TIMER.mark("bwd attention dK|dV")
+                recv = torch.empty((int(sum(pg.send_counts)), f * 2 * d), dtype=torch.bfloat16, device=dev)
+                dist.all_to_all_single(recv, halo, output_split_sizes=pg.send_counts, input_split_sizes=pg.recv_counts,
+                                       group=group)
+                _lib.call("ampconv_halo_add_bf16", recv, pg.add_tgt, pg.add_rowptr, pg.add_pos, d_kv,
+                          _lib.i64(pg.add_tgt.numel()), _lib.i64(f * 2 * d), st)
+                del recv, halo
+            else:
+                d_kv_partial = torch.empty((pg.num_kv_nodes * f, 2 * d), dtype=torch.float32, device=dev)
+                _lib.call("ampconv_attn_bwd_dkv_bf16_part", q, k_all, v_all, d_agg, lse2, delta, g.src_rowptr, g.src_dst,
+                          g.src_pos, g.order_src, d_kv_partial, *tail)
+                TIMER.mark("bwd attention dK|dV")
+                d_kv = d_kv_partial[:rows]
+                if pg.world > 1:
+                    halo_scatter_add(d_kv_partial[rows:].view(pg.n_halo, f * 2 * d), d_kv.view(n, f * 2 * d), pg, group)
+            TIMER.mark("bwd halo exchange dK|dV")
             d_qkv = torch.cat([d_q, d_kv], dim=1)
-            del d_kv_partial
             d_x = torch.empty_like(x_local)
             d_w_in = torch.empty_like(w_in)
             d_b_in = torch.empty(3 * d, dtype=torch.float32, device=dev)
             _lib.call("ampconv_qkv_proj_bwd_input_tc", d_qkv, w_in, d_x, _lib.i64(rows), _lib.i32(d), bws, st)
             _lib.call("ampconv_qkv_proj_bwd_params_tc", x_local, d_qkv, d_w_in, d_b_in, _lib.i64(rows), _lib.i32(d), ws,
                       _lib.size_t(ws.numel()), bws, st)
+            TIMER.mark("bwd qkv projection")
             flat = torch.cat([d_w_in.flatten(), d_b_in, d_w_out.flatten(), d_b_out])
             if pg.world > 1:
                 dist.all_reduce(flat, group=group)
+            TIMER.mark("parameter-gradient all-reduce")
             o = 0
             outs = []
             for t in (d_w_in, d_b_in, d_w_out, d_b_out):

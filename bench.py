@@ -156,7 +156,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -314,7 +314,7 @@ def run_ours(args):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_ours_partitioned(args, spec, world, rank, dev):
@@ -356,6 +356,7 @@ def run_ours_partitioned(args, spec, world, rank, dev):
     for _ in range(args.warmup):
         step(x)
     barrier()
+    D.phase_summary()            # drop the warm-up marks (AMPNET_B200_DIST_TIMING=1)
     launches0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(dev.index) as clocks:
@@ -368,6 +369,9 @@ def run_ours_partitioned(args, spec, world, rank, dev):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
     launches = (_lib.launch_count() - launches0) // max(1, args.steps)
+    phases = D.phase_summary()
+    if phases and rank == 0:
+        sys.stderr.write("phase ms (rank 0): " + json.dumps({k: round(v, 2) for k, v in phases.items()}) + "\n")
 
     # end to end: H2D of this rank's rows of x from pinned memory, fwd, bwd, D2H of loss and parameter gradients
     x_dev = torch.empty_like(x_host, device=dev)
@@ -418,7 +422,7 @@ def run_ours_partitioned(args, spec, world, rank, dev):
         "roofline": {"bound": "hbm", "kernel": "whole step (see the N=1 line for per-kernel numbers)", "achieved": None,
                      "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": None, "traffic": None, "peak_source": pk["source"]},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def profile_attention_kernels(conv, x, edge_index, d_out, mode, reps):
@@ -435,7 +439,27 @@ def profile_attention_kernels(conv, x, edge_index, d_out, mode, reps):
     return stages
 
 
+_REAL_STDOUT = None
+
+
+def _guard_stdout():
+    """Only the JSON line may reach stdout: NCCL and friends print banners to fd 1, so route fd 1 to stderr and keep a
+    private handle on the real stdout for emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

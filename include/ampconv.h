@@ -267,6 +267,21 @@ AMPCONV_API int ampconv_attn_bwd_dkv_bf16_part(const void* q, const void* k, con
                                    int64_t num_nodes, int64_t num_kv_nodes, int64_t num_edges, int F, int d, int H,
                                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* Halo-exchange variants (destination-partitioned multi-GPU, ampnet_b200/distributed.py; no counterpart in the reference,
+ * whose only multi-process code is the unsynchronised gloo demo experiments/cora_benchmark_graphsaint_distributed.py:63,83).
+ * _dkv_bf16_halo: sources [0, num_own) are this rank's nodes -> d_kv_own fp32 [num_own*F, 128]; sources
+ * [num_own, num_kv_nodes) are halo nodes -> partial rows as bf16 in d_kv_halo [(num_kv_nodes-num_own)*F, 128].
+ * ampconv_halo_add_bf16: acc[tgt[i], :] += sum over j in [rowptr[i], rowptr[i+1]) of recv[pos[j], :] (bf16 rows of
+ * row_elems elements, fp32 accumulator rows), in list order: deterministic, no atomics. */
+AMPCONV_API int ampconv_attn_bwd_dkv_bf16_halo(const void* q, const void* k, const void* v, const void* d_agg_bf16,
+                                   const float* lse2, const float* delta, const int32_t* src_rowptr,
+                                   const int32_t* src_dst, const int32_t* src_pos, const int32_t* order,
+                                   float* d_kv_own, void* d_kv_halo, int64_t num_nodes, int64_t num_own,
+                                   int64_t num_kv_nodes, int64_t num_edges, int F, int d, int H,
+                                   void* workspace, size_t workspace_bytes, void* stream);
+AMPCONV_API int ampconv_halo_add_bf16(const void* recv_bf16, const int32_t* tgt, const int32_t* rowptr, const int32_t* pos,
+                          float* acc, int64_t n_tgt, int64_t row_elems, void* stream);
+
 /* Copies the status word of the last bf16 kernel that used `workspace` to the host (0 = ok, otherwise
  * the id of the pipeline wait that timed out).  Synchronises `stream`; meant for tests and debugging. */
 AMPCONV_API int ampconv_bf16_status(const void* workspace, int* status_host, void* stream);
