@@ -4,8 +4,9 @@
     python bench.py --gpus 1 --steps K --warmup W            # our CUDA path
     python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
 
-A "step" is one forward + backward of one AMPConv layer over the whole synthetic graph
-(loss = (out * d_out).sum()).  At N=1 the workload is config C4 of SURVEY.md section 8 (synthetic
+A "step" is one forward + backward of one AMPConv layer over the whole synthetic graph with a fixed
+upstream gradient d_out (out.backward(d_out)); the e2e leg additionally forms the scalar <out, d_out> and reads it
+and the four parameter gradients back to the host.  At N=1 the workload is config C4 of SURVEY.md section 8 (synthetic
 ogbn-arxiv shape: 169 343 nodes, 1 166 243 edges, 128 feature tokens, embed 64, 4 heads), the
 largest configuration of BASELINE.json that fits one GPU.  Inputs are larger than L2 (x alone is
 5.5 GB), so no explicit L2 flush is needed between iterations.
@@ -175,6 +176,17 @@ def algorithmic_bytes(spec, mode):
     }
 
 
+def ncu_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed ncu --set full capture
+    of this workload (profiles/ncu_traffic.json); None when no capture of this workload has been committed."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        t = json.load(open(path)).get(workload)
+        return (int(t["bytes"][kernel]), t["source"]) if t and kernel in t["bytes"] else (None, None)
+    except Exception:
+        return None, None
+
+
 def run_ours(args):
     from ampnet_b200 import AMPConv, _lib
     from ampnet_b200 import functional as F_
@@ -207,13 +219,15 @@ def run_ours(args):
     init_conv(conv)
     params = list(conv.parameters())
 
-    def step(xin, ei):
+    def step(xin, ei, want_loss=False):
+        """One forward + backward of the layer with the upstream gradient d_out (the metric's unit of work).  The scalar
+        loss <out, d_out> is only formed where a result has to travel to the host (the e2e leg)."""
         for p in params:
             p.grad = None
         xin.grad = None
         out = conv(xin, ei)
-        loss = (out * d_out).sum()
-        loss.backward()
+        loss = torch.dot(out.detach().view(-1), d_out.view(-1)) if want_loss else None
+        out.backward(d_out)
         return loss
 
     def barrier():
@@ -254,7 +268,7 @@ def run_ours(args):
         x_dev.copy_(x_host, non_blocking=True)
         ei_dev = ei_host.to(dev, non_blocking=True)
         xin = x_dev.detach().requires_grad_(True)
-        loss = step(xin, ei_dev)
+        loss = step(xin, ei_dev, want_loss=True)
         loss_host.copy_(loss.detach(), non_blocking=True)
         for gh, p in zip(grads_host, params):
             gh.copy_(p.grad, non_blocking=True)
@@ -282,9 +296,16 @@ def run_ours(args):
     pk = peaks()
     dominant = max(kern_ms, key=kern_ms.get)
     achieved = alg[dominant] / (kern_ms[dominant] * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic(args.workload, dominant)
+    # the unit that actually binds these kernels is MUFU (exp2): H*F^2 exponentials per edge and pass at 16 / clk / SM
+    exps = float(e) * h * f * f
+    sm_clk = 148 * 1.965e9
+    mufu = {k: exps / (v * 1e-3) / sm_clk / 16.0 for k, v in kern_ms.items()}
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
-                "kernel_ms": kern_ms, "algorithmic_bytes": alg}
+                "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": pk["source"], "kernel_ms": kern_ms, "algorithmic_bytes": alg,
+                "mufu_frac": {"note": "fraction of the exp2 issue peak (16 per clk per SM at 1.965 GHz, 148 SMs); "
+                                      "the binding pipe of all three kernels at head_dim 16", **mufu}}
 
     if rank != 0:
         return
@@ -339,13 +360,13 @@ def run_ours_partitioned(args, spec, world, rank, dev):
     mha = conv.multi_head_attention
     params = list(conv.parameters())
 
-    def step(xin):
+    def step(xin, want_loss=False):
         for p in params:
             p.grad = None
         xin.grad = None
         out = D.dist_amp_conv(xin, pg, mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight, mha.out_proj.bias, h)
-        loss = (out * d_out).sum()
-        loss.backward()
+        loss = torch.dot(out.detach().view(-1), d_out.view(-1)) if want_loss else None
+        out.backward(d_out)
         return loss
 
     def barrier():
@@ -381,7 +402,7 @@ def run_ours_partitioned(args, spec, world, rank, dev):
     def e2e_step():
         x_dev.copy_(x_host, non_blocking=True)
         xin = x_dev.detach().requires_grad_(True)
-        loss = step(xin)
+        loss = step(xin, want_loss=True)
         loss_host.copy_(loss.detach(), non_blocking=True)
         for gh, p in zip(grads_host, params):
             gh.copy_(p.grad, non_blocking=True)
