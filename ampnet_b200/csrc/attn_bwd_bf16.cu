@@ -37,7 +37,9 @@ using namespace umma;
 constexpr int kD = 64;
 constexpr int kTileBytes = 128 * 128;
 constexpr int kEwWarps = 16;     // elementwise warps: 4 TMEM lane quarters x 4 column groups of 16 score columns
-constexpr int kThreads = (kEwWarps + 4) * 32;   // + producer warp + score-MMA warp + 2 consumer-MMA warps
+constexpr int kFoldWarps = 4;    // MODE_DQ only: one warp per TMEM lane quarter folds delta o (P K) and writes dQ
+// elementwise warps + producer warp + score-MMA warp + 2 consumer-MMA warps (+ fold warps)
+__host__ __device__ constexpr int threads_of(int mode) { return (kEwWarps + 4 + (mode == 0 ? kFoldWarps : 0)) * 32; }
 constexpr int kSets = 3;         // TMEM score sets of 128 columns
 constexpr int kAccCol = 384;     // accumulator block 0 at [384, 448), block 1 at [448, 512)
 constexpr int MODE_DQ = 0, MODE_DKV = 1;
@@ -51,11 +53,12 @@ struct FalseTag { static constexpr bool value = false; };
 
 template <int MODE>
 struct BwdSmem {
-  static constexpr int NS = 4;
+  static constexpr int NS = MODE == MODE_DQ ? 3 : 4;
   uint8_t own[2][2][kTileBytes];        // [slot][tile 0/1]
   uint8_t edge[NS][2][kTileBytes];      // [stage][tile 0/1]
   float stat[MODE == MODE_DKV ? NS : 1][2][kStatFloats];   // MODE_DKV: lse2 / delta rows of the edge
   float dl[8][4][128];                  // MODE_DQ: partial delta of [item & 7][group * 2 + column block][row]
+  float racc[MODE == MODE_DQ ? 64 * 128 : 4];   // MODE_DQ: - sum_e delta_e o (P_e K) of the node, [column][row]
   uint64_t own_full[2], own_empty[2];
   uint64_t edge_full[NS], edge_empty[NS];
   uint64_t xy_full[kSets], set_empty[kSets], op_full[kSets];
@@ -86,7 +89,7 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
 // rowptr/nbr: CSR of the pass (by destination for MODE_DQ, by source for MODE_DKV); slot_of[e] = position of
 // edge e in the statistics arrays (NULL: identity).  d_qkv: fp32 [rows, out_ld].
 template <int HD, int MODE, bool PROF>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(threads_of(MODE), 1)
 attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_constant__ CUtensorMap own1,
                      const __grid_constant__ CUtensorMap oth0, const __grid_constant__ CUtensorMap oth1,
                      const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr,
@@ -107,7 +110,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sm.own_full[i], 1);
-      mbar_init(&sm.own_empty[i], 1 + kEwWarps + 2);
+      mbar_init(&sm.own_empty[i], 1 + kEwWarps + 2 + (MODE == MODE_DQ ? kFoldWarps : 0));
     }
     for (int i = 0; i < kSets; ++i) {
       mbar_init(&sm.xy_full[i], 1);
@@ -121,10 +124,10 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
     for (int i = 0; i < 32; ++i) mbar_init(&sm.dl_bar[i >> 2][i & 3], 4);
     for (int i = 0; i < 4; ++i) {
       mbar_init(&sm.ko_full[i], 1);
-      mbar_init(&sm.ko_empty[i], kEwWarps);
+      mbar_init(&sm.ko_empty[i], kFoldWarps);
     }
     mbar_init(&sm.acc_full, 2);
-    mbar_init(&sm.acc_empty, kEwWarps);
+    mbar_init(&sm.acc_empty, MODE == MODE_DQ ? kFoldWarps : kEwWarps);
     fence_barrier_init();
   }
   if (warp == kEwWarps && lane == 0) {
@@ -143,7 +146,8 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
   // register re-partitioning: the four single-lane control warps give registers to the 16 elementwise warps
   if (warp == kEwWarps) {
     // ------------------------------------------------------------------ producer / scheduler
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    if (MODE == MODE_DQ) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     uint32_t qi = 0, ei = 0;
     for (;;) {
       int node = -1, eb = 0, ee = 0;
@@ -217,7 +221,8 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
     }
   } else if (warp == W_SCORE) {
     // ------------------------------------------------------------------ score MMAs X, Y of every half-item
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    if (MODE == MODE_DQ) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     {
       const uint32_t idesc_xy = idesc_bf16(128, 64, 0, 0);
       uint32_t qi = 0, edge = 0, k = 0;
@@ -261,7 +266,8 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
     //   B = an edge tile as MN-major operand: K / K (MODE_DQ), dO / Q' (MODE_DKV)
     //   destination: MODE_DKV block `which` of the node accumulators; MODE_DQ which = 1 the dQ accumulator,
     //   which = 0 the P K ring slot of the item (fresh per item, folded by the elementwise warps).
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    if (MODE == MODE_DQ) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     {
       const uint32_t which = warp == W_TY ? 1u : 0u;
       const uint32_t idesc_t = idesc_bf16(128, 16, 0, 1);      // N = 16 per MMA (two per K step when hd = 32)
@@ -311,23 +317,96 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
         mma_commit_w(&sm.acc_full);
       }
     }
+  } else if (MODE == MODE_DQ && warp >= kEwWarps + 4) {
+    // ------------------------------------------------------------------ fold warps (MODE_DQ): one per TMEM lane quarter
+    //   per item: delta = sum of the four elementwise partials; racc -= delta o (P K) read from the ring slot; delta is
+    //   written for the dK/dV pass.  Per node: dQ = (TMEM accumulator + racc) * scale.  racc lives in shared memory
+    //   ([column][row], conflict-free) so that these warps run on 56 registers.
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    {
+      const uint32_t q4 = warp & 3;
+      const int row = q4 * 32 + lane;
+      const bool row_ok = row < F;
+      const uint32_t lane_base = tmem + ((uint32_t)(q4 * 32) << 16);
+      constexpr int R = 64 / HD;
+      float* racc = sm.racc + row;                  // column c at racc[c * 128]
+#pragma unroll 8
+      for (int c = 0; c < 64; ++c) racc[c * 128] = 0.f;
+      uint32_t qi = 0, item = 0;
+      for (;; ++qi) {
+        const uint32_t qb = qi & 1;
+        AMP_WAIT(&sm.own_full[qb], (qi >> 1) & 1, 401);
+        const NodeSlot ns = sm.slot[qb];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.own_empty[qb]);
+        if (ns.node < 0) break;
+        float* delta_row = delta + (int64_t)ns.e_begin * H * Fs + row;   // statistics rows of a node's items are consecutive
+        for (int e = ns.e_begin; e < ns.e_end; ++e) {
+#pragma unroll 1
+          for (int h = 0; h < H; ++h, ++item) {
+            const uint32_t slot = item % R;
+            AMP_WAIT(&sm.dl_bar[item & 7][q4], (item >> 3) & 1, 402);
+            const float* dls = &sm.dl[item & 7][0][row];
+            const float dsum = (dls[0] + dls[128]) + (dls[256] + dls[384]);
+            AMP_WAIT(&sm.ko_full[slot], (item / R) & 1, 403);
+            tc_fence_after();
+            float* ra = racc + h * HD * 128;
+#pragma unroll
+            for (int part = 0; part < HD / 16; ++part) {
+              uint32_t ko[16];
+              tmem_ld_32x32b_x16(lane_base + kAccCol + 64 + slot * HD + 16 * part, ko);
+              tmem_ld_wait();
+#pragma unroll
+              for (int x = 0; x < 16; ++x) ra[(16 * part + x) * 128] -= dsum * __uint_as_float(ko[x]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.ko_empty[slot]);
+            if (row_ok) delta_row[0] = dsum;
+            delta_row += Fs;
+          }
+        }
+        // node end: all consumer MMAs of the node have landed in the dQ accumulator
+        AMP_WAIT(&sm.acc_full, qi & 1, 404);
+        tc_fence_after();
+        float* o = d_qkv + ((int64_t)ns.node * F + row) * out_ld + out_c0;
+#pragma unroll 1
+        for (int c4 = 0; c4 < 4; ++c4) {
+          uint32_t a[16];
+          tmem_ld_32x32b_x16(lane_base + kAccCol + 16 * c4, a);
+          tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int x = 0; x < 16; ++x) {
+            v[x] = (__uint_as_float(a[x]) + racc[(16 * c4 + x) * 128]) * out_scale0;
+            racc[(16 * c4 + x) * 128] = 0.f;
+          }
+          if (row_ok) {
+#pragma unroll
+            for (int x = 0; x < 16; x += 4)
+              *reinterpret_cast<float4*>(o + 16 * c4 + x) = make_float4(v[x], v[x + 1], v[x + 2], v[x + 3]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.acc_empty);
+      }
+    }
   } else {
     // ------------------------------------------------------------------ elementwise warps
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    if (MODE == MODE_DQ) asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     const uint32_t q4 = warp & 3;                   // TMEM lane quarter
     const uint32_t grp = warp >> 3;                 // group: works on half-items with k & 1 == grp
     const uint32_t cb = (warp >> 2) & 1;            // column block: score columns [32cb, 32cb+32) of the half
-    const uint32_t j4 = grp * 2 + cb;               // 0..3 within the lane quarter
+    const uint32_t j4 = grp * 2 + cb;               // 0..3 within the lane quarter (delta partial slot / epilogue columns)
     const int row = q4 * 32 + lane;
     const bool row_ok = row < F;
     const uint32_t lane_base = tmem + ((uint32_t)(q4 * 32) << 16);
-    constexpr int R = 64 / HD;                      // P K ring slots (MODE_DQ)
-    constexpr int HQ = HD / 4;                      // P K / dQ columns per head owned by this thread (MODE_DQ)
-    constexpr int DEFER = R - 1;                    // MODE_DQ: items between publishing P and folding delta o (P K)
     uint32_t qi = 0, k = 0, ei = 0, item = 0;
     // light-weight wait accounting (debug entry point only): cycles this warp spent blocked on each kind of barrier
     const bool do_prof = PROF && blockIdx.x == 0 && (warp == 0 || warp == 8);
-    uint32_t wt[6] = {0, 0, 0, 0, 0, 0};
+    uint32_t wt[6] = {0, 0, 0, 0, 0, 0};           // [4], [5] unused since the fold moved to its own warps
     const uint32_t t_begin = do_prof ? (uint32_t)clock() : 0u;
 #define AMP_PHASE(i)
 #define AMP_TWAIT(i, bar, parity, code)                                       \
@@ -347,41 +426,8 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.own_empty[qb]);
       if (ns.node < 0) break;
-      float racc[H][HQ];                             // MODE_DQ: - sum_e delta_e o (P_e K_h), this thread's columns
-#pragma unroll
-      for (int h = 0; h < H; ++h)
-#pragma unroll
-        for (int x = 0; x < HQ; ++x) racc[h][x] = 0.f;
       uint32_t t = 0;                                // items of this node processed so far
       float L_next = 0.f;
-      // MODE_DQ: folds item `it` (head hp, the t-th... of this node at edge slot ep) into racc and frees its ring slot
-      auto fold = [&](uint32_t it, int hp, int ep) -> bool {
-        const uint32_t slot = it % R;
-        const uint32_t tf0 = PROF ? (uint32_t)clock() : 0u;
-        if (!mbar_wait(&sm.dl_bar[it & 7][q4], (it >> 3) & 1)) return false;
-        const uint32_t tf1 = PROF ? (uint32_t)clock() : 0u;
-        if (!mbar_wait(&sm.ko_full[slot], (it / R) & 1)) return false;
-        if (PROF) { wt[4] += tf1 - tf0; wt[5] += (uint32_t)clock() - tf1; }
-        tc_fence_after();
-        uint32_t ko[HQ];
-        if constexpr (HQ == 4) tmem_ld_32x32b_x4(lane_base + kAccCol + 64 + slot * HD + HQ * j4, ko);
-        else tmem_ld_32x32b_x8(lane_base + kAccCol + 64 + slot * HD + HQ * j4, ko);
-        const float* dls = &sm.dl[it & 7][0][row];
-        const float dsum = (dls[0] + dls[128]) + (dls[256] + dls[384]);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.ko_empty[slot]);
-        if (j4 == 0 && row_ok) delta[((int64_t)ep * H + hp) * Fs + row] = dsum;
-        // hp is a run-time value (rolled head loop): select the accumulator row with predicated updates
-#pragma unroll
-        for (int hh = 0; hh < H; ++hh) {
-          const float dsel = hh == hp ? dsum : 0.f;
-#pragma unroll
-          for (int x = 0; x < HQ; ++x) racc[hh][x] -= dsel * __uint_as_float(ko[x]);
-        }
-        return true;
-      };
       for (int e = ns.e_begin; e < ns.e_end; ++e, ++ei) {
         const uint32_t st = ei % NS;
         if (MODE == MODE_DKV) AMP_TWAIT(1, &sm.edge_full[st], (ei / NS) & 1, 306);   // acquire the bulk-copied statistics rows
@@ -389,22 +435,12 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
 #pragma unroll 1
         for (int h = 0; h < H; ++h, ++item, ++t) {
           float L = 0.f;
-          bool folded = true;
           if (MODE == MODE_DQ) {
             // the row statistic of the next item of the node is fetched one item ahead (global-load latency off the path)
             L = t == 0 ? (row_ok ? lse2[((int64_t)e * H + h) * Fs + row] : 0.f) : L_next;
             const bool last = e + 1 == ns.e_end && h == H - 1;
             L_next = (!last && row_ok) ? lse2[((int64_t)e * H + h + 1) * Fs + row] : 0.f;
-            folded = t < DEFER;
           }
-          // MODE_DQ: fold item - DEFER (same node: head (h - DEFER) mod H, an earlier edge slot when DEFER > h)
-          auto fold_now = [&]() -> bool {
-            const int hp = (h + H * DEFER - DEFER) % H;
-            const int ep = e - (DEFER + H - 1 - h) / H;
-            folded = true;
-            return fold(item - DEFER, hp, ep);
-          };
-          if (MODE == MODE_DQ && !folded) { if (!fold_now()) AMP_FAIL(308); }
           const uint32_t ls_addr = smem_u32(sm.stat[MODE == MODE_DKV ? st : 0][0] + h * Fs);
           const uint32_t ds_addr = smem_u32(sm.stat[MODE == MODE_DKV ? st : 0][1] + h * Fs);
           float2 dl2 = make_float2(0.f, 0.f);
@@ -491,47 +527,13 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
           if (lane == 0) mbar_arrive(&sm.edge_empty[st]);   // this warp no longer reads the stage's statistics rows
         }
       }
+      // node epilogue.  MODE_DQ: the fold warps own the accumulators (they add the delta term and write dQ); the
+      // elementwise warps go straight on to the next node.
       if (MODE == MODE_DQ) {
-        // drain: the last min(t, DEFER) items of the node (heads H-2, H-1 of the last edge for H = 4; 0, 1 for H = 2)
-#pragma unroll
-        for (int back = DEFER; back >= 1; --back) {
-          if (t >= (uint32_t)back) {
-            const int hp = (H * DEFER - back) % H;
-            const int ep = ns.e_end - 1 - (back - 1) / H;
-            if (!fold(item - back, hp, ep)) AMP_FAIL(309);
-          }
-        }
-        AMP_PHASE(4);
-      }
-      // node epilogue: all consumer MMAs of the node have landed in the accumulators
-      AMP_TWAIT(3, &sm.acc_full, qi & 1, 304);
-      tc_fence_after();
-      if (MODE == MODE_DQ) {
-        // dQ = TMEM accumulator (sum_e W_e K) + racc; this thread owns columns [h HD + HQ j4, + HQ) of every head
-        uint32_t a[H][HQ];
-#pragma unroll
-        for (int h = 0; h < H; ++h) {
-          if constexpr (HQ == 4) tmem_ld_32x32b_x4(lane_base + kAccCol + h * HD + HQ * j4, a[h]);
-          else tmem_ld_32x32b_x8(lane_base + kAccCol + h * HD + HQ * j4, a[h]);
-        }
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.acc_empty);
-        if (row_ok) {
-          float* o = d_qkv + ((int64_t)ns.node * F + row) * out_ld + out_c0 + HQ * j4;
-#pragma unroll
-          for (int h = 0; h < H; ++h) {
-            float4* o4 = reinterpret_cast<float4*>(o + h * HD);
-#pragma unroll
-            for (int x = 0; x < HQ; x += 4)
-              o4[x >> 2] = make_float4((__uint_as_float(a[h][x]) + racc[h][x]) * out_scale0,
-                                       (__uint_as_float(a[h][x + 1]) + racc[h][x + 1]) * out_scale0,
-                                       (__uint_as_float(a[h][x + 2]) + racc[h][x + 2]) * out_scale0,
-                                       (__uint_as_float(a[h][x + 3]) + racc[h][x + 3]) * out_scale0);
-          }
-        }
       } else {
+        // all consumer MMAs of the node have landed in the accumulators
+        AMP_TWAIT(3, &sm.acc_full, qi & 1, 304);
+        tc_fence_after();
         // block 0 = dV (X-side operand P^T), block 1 = dK (Y-side operand dS^T); this warp owns 32 of the 128 columns
         uint32_t a[32];
         tmem_ld_32x32b_x32(lane_base + kAccCol + 32 * j4, a);
@@ -592,11 +594,11 @@ int launch_bwd(const CUtensorMap& own0, const CUtensorMap& own1, const CUtensorM
   long long* prof = g_bwd_prof;
   if (prof) {
     AMPCONV_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_bf16_kernel<HD, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_bwd_bf16_kernel<HD, MODE, true><<<grid, kThreads, smem, stream>>>(own0, own1, oth0, oth1, rowptr, nbr, slot_of, order, lse2, delta,
+    attn_bwd_bf16_kernel<HD, MODE, true><<<grid, threads_of(MODE), smem, stream>>>(own0, own1, oth0, oth1, rowptr, nbr, slot_of, order, lse2, delta,
                                                                           d_qkv, counter, status, N, F, s0, s1, out_ld, out_c0, out_c1, halo_bf16, halo_from, prof);
   } else {
     AMPCONV_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_bf16_kernel<HD, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_bwd_bf16_kernel<HD, MODE, false><<<grid, kThreads, smem, stream>>>(own0, own1, oth0, oth1, rowptr, nbr, slot_of, order, lse2, delta,
+    attn_bwd_bf16_kernel<HD, MODE, false><<<grid, threads_of(MODE), smem, stream>>>(own0, own1, oth0, oth1, rowptr, nbr, slot_of, order, lse2, delta,
                                                                            d_qkv, counter, status, N, F, s0, s1, out_ld, out_c0, out_c1, halo_bf16, halo_from, nullptr);
   }
   AMPCONV_CHECK_LAUNCH();
