@@ -53,7 +53,7 @@ struct FalseTag { static constexpr bool value = false; };
 
 template <int MODE>
 struct BwdSmem {
-  static constexpr int NS = MODE == MODE_DQ ? 3 : 4;
+  static constexpr int NS = 3;
   uint8_t own[2][2][kTileBytes];        // [slot][tile 0/1]
   uint8_t edge[NS][2][kTileBytes];      // [stage][tile 0/1]
   float stat[MODE == MODE_DKV ? NS : 1][2][kStatFloats];   // MODE_DKV: lse2 / delta rows of the edge
@@ -84,6 +84,18 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
                ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+
+// Debug (PROF kernels only): wait accounting into a local uint32_t wtx[] of the calling role
+#define AMP_XWAIT(i, bar, parity, code)                                       \
+  do {                                                                        \
+    if (PROF) {                                                               \
+      const uint32_t t0_ = (uint32_t)clock();                                 \
+      AMP_WAIT(bar, parity, code);                                            \
+      wtx[i] += (uint32_t)clock() - t0_;                                      \
+    } else {                                                                  \
+      AMP_WAIT(bar, parity, code);                                            \
+    }                                                                         \
+  } while (0)
 
 // own0/own1: tensor maps of the per-node tiles, oth0/oth1: of the per-edge tiles.
 // rowptr/nbr: CSR of the pass (by destination for MODE_DQ, by source for MODE_DKV); slot_of[e] = position of
@@ -273,6 +285,8 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       const uint32_t idesc_t = idesc_bf16(128, 16, 0, 1);      // N = 16 per MMA (two per K step when hd = 32)
       const int btile = (which == 0 && MODE == MODE_DKV) ? 1 : 0;
       const bool ring = MODE == MODE_DQ && which == 0;
+      uint32_t wtx[4] = {0, 0, 0, 0};
+      const uint32_t tx_begin = PROF ? (uint32_t)clock() : 0u;
       constexpr int R = 64 / HD;                                // ring slots
       uint32_t qi = 0, edge = 0, k = 0, item = 0;
       for (;; ++qi) {
@@ -283,7 +297,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
         if (lane == 0) mbar_arrive(&sm.own_empty[qb]);
         if (ns.node < 0) break;
         // the accumulators of the previous node must have been read back
-        AMP_WAIT(&sm.acc_empty, (qi & 1) ^ 1, 212);
+        AMP_XWAIT(0, &sm.acc_empty, (qi & 1) ^ 1, 212);
         for (int e = ns.e_begin; e < ns.e_end; ++e, ++edge) {
           const uint32_t st = edge % NS;
           const uint32_t keep = ring ? 0u : (e != ns.e_begin ? 1u : 0u);
@@ -293,10 +307,10 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
             const uint32_t slot = item % R;
             const uint32_t d_col = ring ? tmem + kAccCol + 64 + slot * HD
                                         : tmem + kAccCol + (MODE == MODE_DKV ? which * 64 : 0) + h * HD;
-            if (ring) AMP_WAIT(&sm.ko_empty[slot], ((item / R) & 1) ^ 1, 214);
+            if (ring) AMP_XWAIT(1, &sm.ko_empty[slot], ((item / R) & 1) ^ 1, 214);
             for (int half = 0; half < nhalf; ++half, ++k) {
               const uint32_t set = k % kSets;
-              AMP_WAIT(&sm.op_full[set], (k / kSets) & 1, 213);
+              AMP_XWAIT(2, &sm.op_full[set], (k / kSets) & 1, 213);
               tc_fence_after();
               const uint32_t a_col = tmem + set * 128 + which * 64;
 #pragma unroll
@@ -316,6 +330,12 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
         }
         mma_commit_w(&sm.acc_full);
       }
+      if (PROF && blockIdx.x == 0 && lane == 0) {
+        long long* pr = prof + 32 + 8 * which;      // [0] accumulators free, [1] ring slot free, [2] operands, [6] total, [7] items
+        for (int i = 0; i < 3; ++i) pr[i] = wtx[i];
+        pr[6] = (uint32_t)clock() - tx_begin;
+        pr[7] = item;
+      }
     }
   } else if (MODE == MODE_DQ && warp >= kEwWarps + 4) {
     // ------------------------------------------------------------------ fold warps (MODE_DQ): one per TMEM lane quarter
@@ -333,9 +353,11 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
 #pragma unroll 8
       for (int c = 0; c < 64; ++c) racc[c * 128] = 0.f;
       uint32_t qi = 0, item = 0;
+      uint32_t wtx[4] = {0, 0, 0, 0};
+      const uint32_t tf_begin = PROF ? (uint32_t)clock() : 0u;
       for (;; ++qi) {
         const uint32_t qb = qi & 1;
-        AMP_WAIT(&sm.own_full[qb], (qi >> 1) & 1, 401);
+        AMP_XWAIT(3, &sm.own_full[qb], (qi >> 1) & 1, 401);
         const NodeSlot ns = sm.slot[qb];
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.own_empty[qb]);
@@ -345,10 +367,10 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
 #pragma unroll 1
           for (int h = 0; h < H; ++h, ++item) {
             const uint32_t slot = item % R;
-            AMP_WAIT(&sm.dl_bar[item & 7][q4], (item >> 3) & 1, 402);
+            AMP_XWAIT(0, &sm.dl_bar[item & 7][q4], (item >> 3) & 1, 402);
             const float* dls = &sm.dl[item & 7][0][row];
             const float dsum = (dls[0] + dls[128]) + (dls[256] + dls[384]);
-            AMP_WAIT(&sm.ko_full[slot], (item / R) & 1, 403);
+            AMP_XWAIT(1, &sm.ko_full[slot], (item / R) & 1, 403);
             tc_fence_after();
             float* ra = racc + h * HD * 128;
 #pragma unroll
@@ -367,7 +389,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
           }
         }
         // node end: all consumer MMAs of the node have landed in the dQ accumulator
-        AMP_WAIT(&sm.acc_full, qi & 1, 404);
+        AMP_XWAIT(2, &sm.acc_full, qi & 1, 404);
         tc_fence_after();
         float* o = d_qkv + ((int64_t)ns.node * F + row) * out_ld + out_c0;
 #pragma unroll 1
@@ -390,6 +412,12 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.acc_empty);
+      }
+      if (PROF && blockIdx.x == 0 && warp == kEwWarps + 4 && lane == 0) {
+        long long* pr = prof + 48;                  // [0] delta partials, [1] P K slot, [2] accumulators, [3] own tiles, [6] total, [7] items
+        for (int i = 0; i < 4; ++i) pr[i] = wtx[i];
+        pr[6] = (uint32_t)clock() - tf_begin;
+        pr[7] = item;
       }
     }
   } else {

@@ -72,6 +72,14 @@ def bwd():
             print(f"bwd {mode} {who}: items={items} total cycles/item={p[off + 6] / items:.0f}; blocked per item on: " +
                   ", ".join(f"{nm} {p[off + i] / items:.0f}" for i, nm in enumerate(names)) +
                   f"; busy {(p[off + 6] - sum(p[off:off + 6])) / items:.0f}")
+        for off, who, nm in ((32, "X-side consumer warp", ["accumulators free", "ring slot free", "operands"]),
+                             (40, "Y-side consumer warp", ["accumulators free", "ring slot free", "operands"]),
+                             (48, "fold warp 0", ["delta partials", "P K slot", "accumulators", "own tiles"])):
+            if p[off + 7] > 0:
+                it = p[off + 7]
+                print(f"    {who}: total/item {p[off + 6] / it:.0f}; blocked on: " +
+                      ", ".join(f"{n_} {p[off + i] / it:.0f}" for i, n_ in enumerate(nm)) +
+                      f"; busy {(p[off + 6] - sum(p[off:off + len(nm)])) / it:.0f}")
 
 
 if __name__ == "__main__":
