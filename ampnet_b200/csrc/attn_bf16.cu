@@ -43,6 +43,17 @@ struct NodeSlot {
   float inv_deg;
 };
 
+// Reads a NodeSlot so that the compiler KNOWS the fields are warp-uniform (shfl from lane 0): the MMA warps' loop counters
+// and descriptor arithmetic then live in uniform registers (a tcgen05.mma issue costs ~10 instructions instead of ~25).
+__device__ __forceinline__ NodeSlot uniform_slot(const NodeSlot& s) {
+  NodeSlot u;
+  u.node = __shfl_sync(0xffffffffu, s.node, 0);
+  u.p_begin = __shfl_sync(0xffffffffu, s.p_begin, 0);
+  u.p_end = __shfl_sync(0xffffffffu, s.p_end, 0);
+  u.inv_deg = __shfl_sync(0xffffffffu, s.inv_deg, 0);
+  return u;
+}
+
 struct FwdSmem {
   // tiles first (1024-byte aligned), then bookkeeping
   uint8_t q[2][kTileBytes];
@@ -109,7 +120,6 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
   const uint32_t tmem = sm.tmem_base;
   // TMEM columns: S[b] = b*128 (fp32 scores), P[b] = 256 + b*64 (bf16 pairs), O[node parity] = 384 + 64*par + h*HD
   const int nqk = ((F + 15) >> 4) << 4;   // MMA N of the score tile
-  const int ksteps = (F + 15) >> 4;       // K steps of P V
 
   if (warp == 8) {
     // ------------------------------------------------------------------ producer / scheduler
@@ -180,7 +190,7 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       for (;; ++qi) {
         const uint32_t qb = qi & 1;
         AMP_WAIT(&sm.q_full[qb], (qi >> 1) & 1, 201);
-        const NodeSlot ns = sm.slot[qb];
+        const NodeSlot ns = uniform_slot(sm.slot[qb]);
         if (ns.node < 0) break;
         for (int p = ns.p_begin; p < ns.p_end; ++p, ++edge) {
           const uint32_t st = edge % kStages;
@@ -212,7 +222,7 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       for (;; ++qi) {
         const uint32_t qb = qi & 1;
         AMP_WAIT(&sm.q_full[qb], (qi >> 1) & 1, 211);
-        const NodeSlot ns = sm.slot[qb];
+        const NodeSlot ns = uniform_slot(sm.slot[qb]);
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.q_empty[qb]);
         if (ns.node < 0) break;
@@ -230,9 +240,10 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
             const uint64_t vdesc = smem_desc(smem_u32(sm.kv[st][1]) + h * (HD * 2), 16, 1024, LAYOUT_SW128);
             const uint32_t o_col = tmem + 384 + par * 64 + h * HD;
             const uint32_t p_col = tmem + 256 + b * 64;
+            // all eight K steps, always: P columns >= F are exact zeros (masked scores) and meet zero-filled V rows
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)
-              if (ks < ksteps) mma_ts_w(o_col, p_col + 8 * ks, desc_advance(vdesc, ks * 2048), idesc_pv, ks > 0 ? 1u : keep);
+              mma_ts_w(o_col, p_col + 8 * ks, desc_advance(vdesc, ks * 2048), idesc_pv, ks > 0 ? 1u : keep);
             mma_commit_w(&sm.p_empty[b]);
           }
           mma_commit_w(&sm.kv_empty[st]);                         // V tile consumed by this warp's heads

@@ -48,6 +48,16 @@ constexpr int kStatFloats = 4 * 128;   // H * roundup4(F) <= 512 floats per edge
 struct NodeSlot {
   int node, e_begin, e_end;
 };
+// Reads a NodeSlot so that the compiler KNOWS the fields are warp-uniform (shfl from lane 0): loop counters and the
+// descriptor / TMEM address arithmetic derived from them can then live in uniform registers, and a tcgen05.mma
+// issue costs a handful of instructions instead of a register-to-uniform broadcast per operand.
+__device__ __forceinline__ NodeSlot uniform_slot(const NodeSlot& s) {
+  NodeSlot u;
+  u.node = __shfl_sync(0xffffffffu, s.node, 0);
+  u.e_begin = __shfl_sync(0xffffffffu, s.e_begin, 0);
+  u.e_end = __shfl_sync(0xffffffffu, s.e_end, 0);
+  return u;
+}
 struct TrueTag { static constexpr bool value = true; };
 struct FalseTag { static constexpr bool value = false; };
 
@@ -241,7 +251,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       for (;; ++qi) {
         const uint32_t qb = qi & 1;
         AMP_WAIT(&sm.own_full[qb], (qi >> 1) & 1, 201);
-        const NodeSlot ns = sm.slot[qb];
+        const NodeSlot ns = uniform_slot(sm.slot[qb]);
         if (ns.node < 0) break;
         for (int e = ns.e_begin; e < ns.e_end; ++e, ++edge) {
           const uint32_t st = edge % NS;
@@ -292,7 +302,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       for (;; ++qi) {
         const uint32_t qb = qi & 1;
         AMP_WAIT(&sm.own_full[qb], (qi >> 1) & 1, 211);
-        const NodeSlot ns = sm.slot[qb];
+        const NodeSlot ns = uniform_slot(sm.slot[qb]);
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.own_empty[qb]);
         if (ns.node < 0) break;
@@ -313,14 +323,13 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
               AMP_XWAIT(2, &sm.op_full[set], (k / kSets) & 1, 213);
               tc_fence_after();
               const uint32_t a_col = tmem + set * 128 + which * 64;
+              // all four K steps, always: score columns >= F carry zero operands and meet zero-filled tile rows
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
-                if (64 * half + 16 * ks < F) {
-                  const uint32_t acc = (half | ks) ? 1u : keep;
+                const uint32_t acc = (half | ks) ? 1u : keep;
 #pragma unroll
-                  for (int part = 0; part < HD / 16; ++part)
-                    mma_ts_w(d_col + 16 * part, a_col + 16 * ks, desc_advance(bd, (4 * half + ks) * 2048 + part * 32), idesc_t, acc);
-                }
+                for (int part = 0; part < HD / 16; ++part)
+                  mma_ts_w(d_col + 16 * part, a_col + 16 * ks, desc_advance(bd, (4 * half + ks) * 2048 + part * 32), idesc_t, acc);
               }
               mma_commit_w(&sm.set_empty[set]);
             }
@@ -358,7 +367,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       for (;; ++qi) {
         const uint32_t qb = qi & 1;
         AMP_XWAIT(3, &sm.own_full[qb], (qi >> 1) & 1, 401);
-        const NodeSlot ns = sm.slot[qb];
+        const NodeSlot ns = uniform_slot(sm.slot[qb]);
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.own_empty[qb]);
         if (ns.node < 0) break;
