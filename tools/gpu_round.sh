@@ -1,5 +1,6 @@
 #!/bin/bash
-# One GPU-box session: GPU tests, phase timers, bench, ncu launch list and a full capture of the attention kernels.
+# One GPU-box session: GPU tests, phase timers, bench, ncu launch list and full captures of the attention kernels
+# (C4s = 1/10-scale workload for the launch list / source-level capture, C4 for the per-launch DRAM traffic).
 # usage: tools/gpu_round.sh <tag>
 tag=${1:-x}
 mkdir -p gpurun_out
@@ -11,4 +12,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python bench.py --workload C4s --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu1_$tag.log 2>&1; echo "ncu1 rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:attn_ -s 9 -c 3 -o gpurun_out/prof_attn_$tag \
     python bench.py --workload C4s --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu2_$tag.log 2>&1; echo "ncu2 rc=$?"
+python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/plain_c4_$tag.log 2>&1 &&
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:attn_ -s 9 -c 3 --csv \
+    --log-file gpurun_out/traffic_c4_$tag.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu3_$tag.log 2>&1; echo "ncu3 rc=$?"
 ls -la gpurun_out | tail -8
