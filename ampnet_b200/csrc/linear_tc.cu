@@ -5,10 +5,10 @@
 // and their input gradients, executed once per node token instead of once per edge token.
 //
 // One persistent kernel, warp-specialised:
-//   warps 0-3  loaders : coalesced fp32 loads of a 128-row tile, convert to bf16, store into the 128B-swizzled
+//   warps 0-7  loaders : coalesced fp32 loads of a 128-row tile, convert to bf16, store into the 128B-swizzled
 //                        K-major layout tcgen05 expects (3-stage ring);
-//   warp  4    MMA     : one thread issues M=128, N, K/16 tcgen05.mma per tile into one of two TMEM accumulators;
-//   warps 5-8  epilogue: tcgen05.ld the accumulator rows, fused bias / gate / row scale / q scaling, bf16 or fp32 stores.
+//   warp  8    MMA     : one thread issues M=128, N, K/16 tcgen05.mma per tile into one of two TMEM accumulators;
+//   warps 9-12 epilogue: tcgen05.ld the accumulator rows, fused bias / gate / row scale / q scaling, bf16 or fp32 stores.
 // The weight matrix is converted once per CTA and stays in shared memory.
 #include <cuda_bf16.h>
 
@@ -20,7 +20,10 @@ namespace {
 
 using namespace umma;
 
-constexpr int kThreads = 288;
+constexpr int kLoadWarps = 8;                      // loader warps: enough loads in flight per SM to cover the HBM latency
+constexpr int kLoadThreads = kLoadWarps * 32;
+constexpr int kMmaWarp = kLoadWarps;               // then the MMA warp, then four epilogue warps (one per TMEM lane quarter)
+constexpr int kThreads = (kLoadWarps + 5) * 32;
 constexpr int kStages = 3;
 
 enum : int { EPI_QKV = 0, EPI_OUT = 1, EPI_DAGG = 2, EPI_DX = 3 };
@@ -56,10 +59,10 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearArgs
   constexpr bool kTransposedW = (EPI == EPI_DAGG || EPI == EPI_DX);
   constexpr int kTmemCols = 512;
 
-  if (warp == 4) tmem_alloc(&sm.tmem_base, kTmemCols);
+  if (warp == kMmaWarp) tmem_alloc(&sm.tmem_base, kTmemCols);
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(&sm.a_full[i], 4);
+      mbar_init(&sm.a_full[i], kLoadWarps);
       mbar_init(&sm.a_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -82,10 +85,10 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearArgs
   const uint32_t tmem = sm.tmem_base;
   const int64_t num_tiles = (args.rows + 127) / 128;
 
-  if (warp < 4) {
+  if (warp < kLoadWarps) {
     // ------------------------------------------------------------------ loaders
     constexpr int kChunksPerRow = K / 8;                 // 16-byte bf16 chunks (8 elements) per row
-    constexpr int kChunksPerThread = kChunksPerRow;      // 128 rows * K/8 chunks / 128 threads
+    constexpr int kChunksPerThread = 128 * kChunksPerRow / kLoadThreads;
     const int tid = threadIdx.x;
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -97,7 +100,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearArgs
       for (int base = 0; base < kChunksPerThread; base += 8) {
 #pragma unroll
         for (int u = 0; u < 8 && base + u < kChunksPerThread; ++u) {
-          const int q = (base + u) * 128 + tid;
+          const int q = (base + u) * kLoadThreads + tid;
           const int r = q / kChunksPerRow, c = q - r * kChunksPerRow;
           const int64_t grow = row0 + r;
           if (grow < args.rows) {
@@ -111,7 +114,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearArgs
         }
 #pragma unroll
         for (int u = 0; u < 8 && base + u < kChunksPerThread; ++u) {
-          const int q = (base + u) * 128 + tid;
+          const int q = (base + u) * kLoadThreads + tid;
           const int r = q / kChunksPerRow, c = q - r * kChunksPerRow;
           uint4 pk;
           pk.x = pack_bf16x2(v[u][0].x, v[u][0].y);
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearArgs
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.a_full[st]);
     }
-  } else if (warp == 4) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
     {
       const uint32_t idesc = idesc_bf16(128, N, 0, 0);
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearArgs
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, kTmemCols);
+  if (warp == kMmaWarp) tmem_dealloc(tmem, kTmemCols);
 }
 
 template <int K, int N, int EPI>
