@@ -35,3 +35,50 @@ def load_message_passing_kat():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
+
+
+def load_amp_gcn_module():
+    """The reference's 2-layer model ``src/ampnet/module/amp_gcn.py`` (``AMPGCN``), loaded by path, unmodified
+    (SURVEY.md Appendix A step 3): plotting libraries are mocked, ``torch_geometric.datasets.Planetoid`` and
+    ``torch_geometric.utils.dropout.dropout_adj`` are stand-ins (``dropout_adj`` is the identity for p = 0 or eval, the only
+    configurations the goldens use), and the ``src.ampnet`` package modules are registered by hand so that the package
+    ``__init__`` (which needs ``umap``) never runs."""
+    import sys
+    import types
+    from unittest.mock import MagicMock
+    if not available():
+        raise FileNotFoundError(_AMP_CONV)
+    pkg = pyg_stub.install()
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.lines", "seaborn"):
+        sys.modules.setdefault(name, MagicMock())
+    ds = types.ModuleType("torch_geometric.datasets")
+    ds.Planetoid = MagicMock()
+    ut = types.ModuleType("torch_geometric.utils")
+    dr = types.ModuleType("torch_geometric.utils.dropout")
+
+    def dropout_adj(edge_index, p=0.5, training=True, **kw):
+        if p == 0.0 or not training:
+            return edge_index, None
+        raise NotImplementedError("stand-in covers p = 0 / eval only")
+
+    dr.dropout_adj = dropout_adj
+    ut.dropout = dr
+    pkg.datasets, pkg.utils = ds, ut
+    sys.modules.update({"torch_geometric.datasets": ds, "torch_geometric.utils": ut, "torch_geometric.utils.dropout": dr})
+    root = os.path.join(REFERENCE_ROOT, "src", "ampnet")
+    for name in ("src", "src.ampnet", "src.ampnet.conv", "src.ampnet.utils", "src.ampnet.module"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = []
+            sys.modules[name] = m
+
+    def load(dotted, rel):
+        spec = importlib.util.spec_from_file_location(dotted, os.path.join(root, rel))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[dotted] = mod
+        spec.loader.exec_module(mod)
+        return mod
+
+    load("src.ampnet.conv.amp_conv", os.path.join("conv", "amp_conv.py"))
+    load("src.ampnet.utils.utils", os.path.join("utils", "utils.py"))
+    return load("src.ampnet.module.amp_gcn", os.path.join("module", "amp_gcn.py"))
