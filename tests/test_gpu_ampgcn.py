@@ -58,3 +58,22 @@ def test_ampgcn_own_sampler_draws_present_features_only():
     idx = model.sampled_node_feat_indices
     assert idx.shape == (50, 5)
     assert bool((x.numpy()[np.arange(50)[:, None], idx] != 0).all())
+
+
+def test_graphsaint_training_on_cora_shaped_graph_learns():
+    """Config 2 of BASELINE.json in miniature: a few GraphSAINT iterations of the 2-layer model on a Cora-shaped graph;
+    the node-normalised training loss must go down and the sampled subgraphs must be consistent."""
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "experiments", "cora_graphsaint_b200.py")
+    spec = importlib.util.spec_from_file_location("cora_graphsaint_b200", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    from ampnet_b200.loader import cora_shaped_data
+    data = cora_shaped_data(num_nodes=600, num_features=140, num_undirected_edges=1500, nnz_per_node=8, num_train=200,
+                            num_val=100, num_test=200, seed=3)
+    model, hist = mod.train(iters=40, batch_size=4, walk_length=40, num_steps=20, sample_coverage=10, lr=0.01, seed=3,
+                            embedding_dim=32, num_heads=4, num_sampled_vectors=8, mode="fp32", data=data, quiet=True)
+    losses = np.array([h[0] for h in hist])
+    assert np.isfinite(losses).all()
+    assert losses[-10:].mean() < 0.8 * losses[:10].mean()
+    assert all(h[2] > 0 and h[3] >= 0 for h in hist)
