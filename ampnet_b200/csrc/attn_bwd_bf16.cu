@@ -88,6 +88,12 @@ struct BwdSmem {
   do {                                                      \
     if (!mbar_wait((bar), (parity))) AMP_FAIL(code);        \
   } while (0)
+// same, barrier given by its shared-space address (sm32 + constant offset: no address arithmetic at the use)
+#define AMP_WAIT_A(addr, parity, code)                      \
+  do {                                                      \
+    if (!mbar_wait_a((addr), (parity))) AMP_FAIL(code);     \
+  } while (0)
+#define SM_OFF(member) (sm32 + (uint32_t)offsetof(Smem, member))
 
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -100,10 +106,10 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
   do {                                                                        \
     if (PROF) {                                                               \
       const uint32_t t0_ = (uint32_t)clock();                                 \
-      AMP_WAIT(bar, parity, code);                                            \
+      AMP_WAIT_A(bar, parity, code);                                          \
       wtx[i] += (uint32_t)clock() - t0_;                                      \
     } else {                                                                  \
-      AMP_WAIT(bar, parity, code);                                            \
+      AMP_WAIT_A(bar, parity, code);                                          \
     }                                                                         \
   } while (0)
 
@@ -124,6 +130,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
   constexpr int H = kD / HD;
   extern __shared__ uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sm32 = smem_base_opaque(&sm);   // shared-space address of sm, held in a register by the hot loops
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Fs = (F + 3) & ~3;   // row stride of the statistics arrays
   constexpr int W_SCORE = kEwWarps + 1, W_TX = kEwWarps + 2, W_TY = kEwWarps + 3;
@@ -307,7 +314,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
         if (lane == 0) mbar_arrive(&sm.own_empty[qb]);
         if (ns.node < 0) break;
         // the accumulators of the previous node must have been read back
-        AMP_XWAIT(0, &sm.acc_empty, (qi & 1) ^ 1, 212);
+        AMP_XWAIT(0, SM_OFF(acc_empty), (qi & 1) ^ 1, 212);
         for (int e = ns.e_begin; e < ns.e_end; ++e, ++edge) {
           const uint32_t st = edge % NS;
           const uint32_t keep = ring ? 0u : (e != ns.e_begin ? 1u : 0u);
@@ -317,10 +324,10 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
             const uint32_t slot = item % R;
             const uint32_t d_col = ring ? tmem + kAccCol + 64 + slot * HD
                                         : tmem + kAccCol + (MODE == MODE_DKV ? which * 64 : 0) + h * HD;
-            if (ring) AMP_XWAIT(1, &sm.ko_empty[slot], ((item / R) & 1) ^ 1, 214);
+            if (ring) AMP_XWAIT(1, SM_OFF(ko_empty) + 8 * slot, ((item / R) & 1) ^ 1, 214);
             for (int half = 0; half < nhalf; ++half, ++k) {
               const uint32_t set = k % kSets;
-              AMP_XWAIT(2, &sm.op_full[set], (k / kSets) & 1, 213);
+              AMP_XWAIT(2, SM_OFF(op_full) + 8 * set, (k / kSets) & 1, 213);
               tc_fence_after();
               const uint32_t a_col = tmem + set * 128 + which * 64;
               // all four K steps, always: score columns >= F carry zero operands and meet zero-filled tile rows
@@ -358,15 +365,15 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       const bool row_ok = row < F;
       const uint32_t lane_base = tmem + ((uint32_t)(q4 * 32) << 16);
       constexpr int R = 64 / HD;
-      float* racc = sm.racc + row;                  // column c at racc[c * 128]
+      const uint32_t racc = SM_OFF(racc) + 4 * row;   // column c at racc + 512 c (shared-space addresses: LDS / STS)
 #pragma unroll 8
-      for (int c = 0; c < 64; ++c) racc[c * 128] = 0.f;
+      for (int c = 0; c < 64; ++c) sts_f32(racc + 512 * c, 0.f);
       uint32_t qi = 0, item = 0;
       uint32_t wtx[4] = {0, 0, 0, 0};
       const uint32_t tf_begin = PROF ? (uint32_t)clock() : 0u;
       for (;; ++qi) {
         const uint32_t qb = qi & 1;
-        AMP_XWAIT(3, &sm.own_full[qb], (qi >> 1) & 1, 401);
+        AMP_XWAIT(3, SM_OFF(own_full) + 8 * qb, (qi >> 1) & 1, 401);
         const NodeSlot ns = uniform_slot(sm.slot[qb]);
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.own_empty[qb]);
@@ -376,29 +383,32 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
 #pragma unroll 1
           for (int h = 0; h < H; ++h, ++item) {
             const uint32_t slot = item % R;
-            AMP_XWAIT(0, &sm.dl_bar[item & 7][q4], (item >> 3) & 1, 402);
-            const float* dls = &sm.dl[item & 7][0][row];
-            const float dsum = (dls[0] + dls[128]) + (dls[256] + dls[384]);
-            AMP_XWAIT(1, &sm.ko_full[slot], (item / R) & 1, 403);
+            AMP_XWAIT(0, SM_OFF(dl_bar) + 32 * (item & 7) + 8 * q4, (item >> 3) & 1, 402);
+            const uint32_t dls = SM_OFF(dl) + 2048 * (item & 7) + 4 * row;
+            const float dsum = (lds_f32(dls) + lds_f32(dls + 512)) + (lds_f32(dls + 1024) + lds_f32(dls + 1536));
+            AMP_XWAIT(1, SM_OFF(ko_full) + 8 * slot, (item / R) & 1, 403);
             tc_fence_after();
-            float* ra = racc + h * HD * 128;
+            const uint32_t ra = racc + h * HD * 512;
 #pragma unroll
             for (int part = 0; part < HD / 16; ++part) {
               uint32_t ko[16];
               tmem_ld_32x32b_x16(lane_base + kAccCol + 64 + slot * HD + 16 * part, ko);
               tmem_ld_wait();
 #pragma unroll
-              for (int x = 0; x < 16; ++x) ra[(16 * part + x) * 128] -= dsum * __uint_as_float(ko[x]);
+              for (int x = 0; x < 16; ++x) {
+                const uint32_t a = ra + (16 * part + x) * 512;
+                sts_f32(a, fmaf(-dsum, __uint_as_float(ko[x]), lds_f32(a)));
+              }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.ko_empty[slot]);
+            if (lane == 0) mbar_arrive_a(SM_OFF(ko_empty) + 8 * slot);
             if (row_ok) delta_row[0] = dsum;
             delta_row += Fs;
           }
         }
         // node end: all consumer MMAs of the node have landed in the dQ accumulator
-        AMP_XWAIT(2, &sm.acc_full, qi & 1, 404);
+        AMP_XWAIT(2, SM_OFF(acc_full), qi & 1, 404);
         tc_fence_after();
         float* o = d_qkv + ((int64_t)ns.node * F + row) * out_ld + out_c0;
 #pragma unroll 1
@@ -409,8 +419,8 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
           float v[16];
 #pragma unroll
           for (int x = 0; x < 16; ++x) {
-            v[x] = (__uint_as_float(a[x]) + racc[(16 * c4 + x) * 128]) * out_scale0;
-            racc[(16 * c4 + x) * 128] = 0.f;
+            v[x] = (__uint_as_float(a[x]) + lds_f32(racc + (16 * c4 + x) * 512)) * out_scale0;
+            sts_f32(racc + (16 * c4 + x) * 512, 0.f);
           }
           if (row_ok) {
 #pragma unroll
@@ -450,42 +460,49 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
   do {                                                                        \
     if (PROF) {                                                               \
       const uint32_t t0_ = (uint32_t)clock();                                 \
-      AMP_WAIT(bar, parity, code);                                            \
+      AMP_WAIT_A(bar, parity, code);                                          \
       wt[i] += (uint32_t)clock() - t0_;                                       \
     } else {                                                                  \
-      AMP_WAIT(bar, parity, code);                                            \
+      AMP_WAIT_A(bar, parity, code);                                          \
     }                                                                         \
   } while (0)
     for (;;) {
       const uint32_t qb = qi & 1;
-      AMP_TWAIT(0, &sm.own_full[qb], (qi >> 1) & 1, 301);
+      AMP_TWAIT(0, SM_OFF(own_full) + 8 * qb, (qi >> 1) & 1, 301);
       const NodeSlot ns = sm.slot[qb];
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.own_empty[qb]);
+      if (lane == 0) mbar_arrive_a(SM_OFF(own_empty) + 8 * qb);
       if (ns.node < 0) break;
       uint32_t t = 0;                                // items of this node processed so far
       float L_next = 0.f;
+      // MODE_DQ: the statistics rows of a node's items are consecutive; running pointer to this thread's next row statistic
+      const float* lse_row = lse2 + (int64_t)ns.e_begin * H * Fs + row;
       for (int e = ns.e_begin; e < ns.e_end; ++e, ++ei) {
         const uint32_t st = ei % NS;
-        if (MODE == MODE_DKV) AMP_TWAIT(1, &sm.edge_full[st], (ei / NS) & 1, 306);   // acquire the bulk-copied statistics rows
+        if (MODE == MODE_DKV) AMP_TWAIT(1, SM_OFF(edge_full) + 8 * st, (ei / NS) & 1, 306);   // acquire the bulk-copied statistics rows
         // NOT unrolled: one copy of the body keeps the elementwise loop inside the instruction cache
 #pragma unroll 1
         for (int h = 0; h < H; ++h, ++item, ++t) {
           float L = 0.f;
           if (MODE == MODE_DQ) {
             // the row statistic of the next item of the node is fetched one item ahead (global-load latency off the path)
-            L = t == 0 ? (row_ok ? lse2[((int64_t)e * H + h) * Fs + row] : 0.f) : L_next;
+            L = t == 0 ? (row_ok ? lse_row[0] : 0.f) : L_next;
             const bool last = e + 1 == ns.e_end && h == H - 1;
-            L_next = (!last && row_ok) ? lse2[((int64_t)e * H + h + 1) * Fs + row] : 0.f;
+            lse_row += Fs;
+            L_next = (!last && row_ok) ? lse_row[0] : 0.f;
           }
-          const uint32_t ls_addr = smem_u32(sm.stat[MODE == MODE_DKV ? st : 0][0] + h * Fs);
-          const uint32_t ds_addr = smem_u32(sm.stat[MODE == MODE_DKV ? st : 0][1] + h * Fs);
+          const uint32_t ls_addr = SM_OFF(stat) + (uint32_t)(((MODE == MODE_DKV ? st : 0) * 2 * kStatFloats + h * Fs) * 4);
+          const uint32_t ds_addr = ls_addr + kStatFloats * 4;
           float2 dl2 = make_float2(0.f, 0.f);
           AMP_PHASE(5);
-          for (int half = 0; half < nhalf; ++half, ++k) {
-            if ((k & 1) != grp) continue;
-            const uint32_t set = k % kSets;
-            AMP_TWAIT(2, &sm.xy_full[set], (k / kSets) & 1, 302);
+          // this group's half-item of the item: with two halves per item the item starts at an even k and group g owns
+          // half g; with one half per item the groups alternate items
+          const int half = nhalf == 2 ? (int)grp : 0;
+          const uint32_t kk = k + half;
+          k += nhalf;
+          if (nhalf == 2 || (kk & 1) == grp) {
+            const uint32_t set = kk % kSets;
+            AMP_TWAIT(2, SM_OFF(xy_full) + 8 * set, (kk / kSets) & 1, 302);
             tc_fence_after();
             const uint32_t xbase = lane_base + set * 128 + 32 * cb;
             uint32_t xs[2][16], ys[2][16];
@@ -548,20 +565,20 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.op_full[set]);
+            if (lane == 0) mbar_arrive_a(SM_OFF(op_full) + 8 * set);
             AMP_PHASE(2);
           }
           if (MODE == MODE_DQ) {
             // partial delta of this warp's columns (zero when the item had no half-item for this group)
-            sm.dl[item & 7][j4][row] = dl2.x + dl2.y;
+            sts_f32(SM_OFF(dl) + 2048 * (item & 7) + 512 * j4 + 4 * row, dl2.x + dl2.y);
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.dl_bar[item & 7][q4]);
+            if (lane == 0) mbar_arrive_a(SM_OFF(dl_bar) + 32 * (item & 7) + 8 * q4);
             AMP_PHASE(3);
           }
         }
         if (MODE == MODE_DKV) {
           __syncwarp();
-          if (lane == 0) mbar_arrive(&sm.edge_empty[st]);   // this warp no longer reads the stage's statistics rows
+          if (lane == 0) mbar_arrive_a(SM_OFF(edge_empty) + 8 * st);   // this warp no longer reads the stage's statistics rows
         }
       }
       // node epilogue.  MODE_DQ: the fold warps own the accumulators (they add the delta term and write dQ); the
@@ -569,7 +586,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       if (MODE == MODE_DQ) {
       } else {
         // all consumer MMAs of the node have landed in the accumulators
-        AMP_TWAIT(3, &sm.acc_full, qi & 1, 304);
+        AMP_TWAIT(3, SM_OFF(acc_full), qi & 1, 304);
         tc_fence_after();
         // block 0 = dV (X-side operand P^T), block 1 = dK (Y-side operand dS^T); this warp owns 32 of the 128 columns
         uint32_t a[32];
@@ -577,7 +594,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.acc_empty);
+        if (lane == 0) mbar_arrive_a(SM_OFF(acc_empty));
         if (row_ok) {
           const bool is_dv = j4 < 2;
           const float sc = is_dv ? out_scale1 : out_scale0;

@@ -44,17 +44,57 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// The *_a variants take the barrier's 32-bit shared-space address.  Hot loops compute the address of their shared
+// structure once (kept opaque to the compiler, see smem_base_opaque) and add constant offsets: the generic-pointer
+// forms re-derive the shared window address (about ten uniform-datapath instructions) at every use.
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(bar), "r"(parity)
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or the hint (ns) elapses,
+// instead of returning after a short system-dependent slice -- a waiting warp then costs (almost) no issue slots.
+__device__ __forceinline__ bool mbar_try_wait_hint_a(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
+// Waits until the phase with the given parity completes.  The wait is bounded (budget_ns of wall
+// time, default 0.25 s) so that a protocol bug turns into a reported failure (returns false)
+// instead of a hung GPU; legitimate waits in these kernels last microseconds.  The clock is only read every
+// 64th retry: a retry is then four instructions instead of fourteen.
+__device__ __forceinline__ bool mbar_wait_a(uint32_t bar, uint32_t parity, uint64_t budget_ns = 250000000ull) {
+  if (mbar_try_wait_a(bar, parity)) return true;
+  const uint64_t t0 = global_timer_ns();
+#pragma unroll 1
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 64; ++i)
+      if (mbar_try_wait_hint_a(bar, parity, 200000u)) return true;
+    if (global_timer_ns() - t0 > budget_ns) return false;
+  }
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) { return mbar_try_wait_a(smem_u32(bar), parity); }
 // Non-blocking probe (try_wait may suspend the thread for a system-dependent time slice; pollers that
 // watch several barriers at once must use this one).
 __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
@@ -68,35 +108,26 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ uint64_t global_timer_ns() {
-  uint64_t t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or the hint (ns) elapses,
-// instead of returning after a short system-dependent slice -- a waiting warp then costs (almost) no issue slots.
 __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
-      : "memory");
-  return ok != 0;
+  return mbar_try_wait_hint_a(smem_u32(bar), parity, hint_ns);
 }
-// Waits until the phase with the given parity completes.  The wait is bounded (budget_ns of wall
-// time, default 0.25 s) so that a protocol bug turns into a reported failure (returns false)
-// instead of a hung GPU; legitimate waits in these kernels last microseconds.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, uint64_t budget_ns = 250000000ull) {
-  if (mbar_try_wait(bar, parity)) return true;
-  const uint64_t t0 = global_timer_ns();
-#pragma unroll 1
-  for (;;) {
-    if (mbar_try_wait_hint(bar, parity, 200000u)) return true;
-    if (global_timer_ns() - t0 > budget_ns) return false;
-  }
+  return mbar_wait_a(smem_u32(bar), parity, budget_ns);
+}
+// Shared-space address of a shared-memory object, made opaque so that the compiler keeps it in a register instead of
+// re-deriving it from the generic pointer at every use.
+__device__ __forceinline__ uint32_t smem_base_opaque(const void* p) {
+  uint32_t a;
+  asm volatile("mov.u32 %0, %1;" : "=r"(a) : "r"(smem_u32(p)));
+  return a;
+}
+__device__ __forceinline__ float lds_f32(uint32_t smem_addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t smem_addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_addr), "f"(v) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------
