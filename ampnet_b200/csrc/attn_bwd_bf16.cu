@@ -66,7 +66,8 @@ struct BwdSmem {
   static constexpr int NS = 3;
   uint8_t own[2][2][kTileBytes];        // [slot][tile 0/1]
   uint8_t edge[NS][2][kTileBytes];      // [stage][tile 0/1]
-  float stat[MODE == MODE_DKV ? NS : 1][2][kStatFloats];   // MODE_DKV: lse2 / delta rows of the edge
+  static constexpr int NSTAT = MODE == MODE_DKV ? 2 : 1;
+  float stat[NS][NSTAT][kStatFloats];   // lse2 (both modes) / delta (MODE_DKV) rows of the edge, bulk-copied by the producer
   float dl[8][4][128];                  // MODE_DQ: partial delta of [item & 7][group * 2 + column block][row]
   float racc[MODE == MODE_DQ ? 64 * 128 : 4];   // MODE_DQ: - sum_e delta_e o (P_e K) of the node, [column][row]
   uint64_t own_full[2], own_empty[2];
@@ -116,7 +117,7 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
 // own0/own1: tensor maps of the per-node tiles, oth0/oth1: of the per-edge tiles.
 // rowptr/nbr: CSR of the pass (by destination for MODE_DQ, by source for MODE_DKV); slot_of[e] = position of
 // edge e in the statistics arrays (NULL: identity).  d_qkv: fp32 [rows, out_ld].
-template <int HD, int MODE, bool PROF>
+template <int HD, int MODE, int NH, bool PROF>
 __global__ void __launch_bounds__(threads_of(MODE), 1)
 attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_constant__ CUtensorMap own1,
                      const __grid_constant__ CUtensorMap oth0, const __grid_constant__ CUtensorMap oth1,
@@ -148,7 +149,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
     }
     for (int i = 0; i < NS; ++i) {
       mbar_init(&sm.edge_full[i], 1);
-      mbar_init(&sm.edge_empty[i], MODE == MODE_DKV ? 3 + kEwWarps : 3);
+      mbar_init(&sm.edge_empty[i], 3 + kEwWarps);
     }
     for (int i = 0; i < 32; ++i) mbar_init(&sm.dl_bar[i >> 2][i & 3], 4);
     for (int i = 0; i < 4; ++i) {
@@ -169,7 +170,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
-  const int nhalf = F > 64 ? 2 : 1;                  // halves with at least one valid score column
+  constexpr int nhalf = NH;                          // halves with at least one valid score column (2 when F > 64)
   const uint32_t stat_bytes = (uint32_t)(H * Fs * sizeof(float));
 
   // register re-partitioning: the four single-lane control warps give registers to the 16 elementwise warps
@@ -235,7 +236,8 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
                 bulk_load(sm.stat[st][0], lse2 + sl * H * Fs, stat_bytes, &sm.edge_full[st]);
                 bulk_load(sm.stat[st][1], delta + sl * H * Fs, stat_bytes, &sm.edge_full[st]);
               } else {
-                mbar_arrive_expect_tx(&sm.edge_full[st], 2 * kTileBytes);
+                mbar_arrive_expect_tx(&sm.edge_full[st], 2 * kTileBytes + stat_bytes);
+                bulk_load(sm.stat[st][0], lse2 + (int64_t)e * H * Fs, stat_bytes, &sm.edge_full[st]);
               }
               tma_load_3d(sm.edge[st][0], &oth0, &sm.edge_full[st], 0, 0, nb);
               tma_load_3d(sm.edge[st][1], &oth1, &sm.edge_full[st], 0, 0, nb);
@@ -473,26 +475,16 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive_a(SM_OFF(own_empty) + 8 * qb);
       if (ns.node < 0) break;
-      uint32_t t = 0;                                // items of this node processed so far
-      float L_next = 0.f;
-      // MODE_DQ: the statistics rows of a node's items are consecutive; running pointer to this thread's next row statistic
-      const float* lse_row = lse2 + (int64_t)ns.e_begin * H * Fs + row;
       for (int e = ns.e_begin; e < ns.e_end; ++e, ++ei) {
         const uint32_t st = ei % NS;
-        if (MODE == MODE_DKV) AMP_TWAIT(1, SM_OFF(edge_full) + 8 * st, (ei / NS) & 1, 306);   // acquire the bulk-copied statistics rows
+        AMP_TWAIT(1, SM_OFF(edge_full) + 8 * st, (ei / NS) & 1, 306);   // acquire the bulk-copied statistics rows
         // NOT unrolled: one copy of the body keeps the elementwise loop inside the instruction cache
 #pragma unroll 1
-        for (int h = 0; h < H; ++h, ++item, ++t) {
-          float L = 0.f;
-          if (MODE == MODE_DQ) {
-            // the row statistic of the next item of the node is fetched one item ahead (global-load latency off the path)
-            L = t == 0 ? (row_ok ? lse_row[0] : 0.f) : L_next;
-            const bool last = e + 1 == ns.e_end && h == H - 1;
-            lse_row += Fs;
-            L_next = (!last && row_ok) ? lse_row[0] : 0.f;
-          }
-          const uint32_t ls_addr = SM_OFF(stat) + (uint32_t)(((MODE == MODE_DKV ? st : 0) * 2 * kStatFloats + h * Fs) * 4);
+        for (int h = 0; h < H; ++h, ++item) {
+          const uint32_t ls_addr = SM_OFF(stat) + (uint32_t)((st * Smem::NSTAT * kStatFloats + h * Fs) * 4);
           const uint32_t ds_addr = ls_addr + kStatFloats * 4;
+          // MODE_DQ: this thread's row statistic (rows >= F read stale shared memory: they only reach discarded output rows)
+          const float L = MODE == MODE_DQ ? lds_f32(ls_addr + 4 * row) : 0.f;
           float2 dl2 = make_float2(0.f, 0.f);
           AMP_PHASE(5);
           // this group's half-item of the item: with two halves per item the item starts at an even k and group g owns
@@ -576,10 +568,8 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
             AMP_PHASE(3);
           }
         }
-        if (MODE == MODE_DKV) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive_a(SM_OFF(edge_empty) + 8 * st);   // this warp no longer reads the stage's statistics rows
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_a(SM_OFF(edge_empty) + 8 * st);   // this warp no longer reads the stage's statistics rows
       }
       // node epilogue.  MODE_DQ: the fold warps own the accumulators (they add the delta term and write dQ); the
       // elementwise warps go straight on to the next node.
@@ -646,15 +636,22 @@ int launch_bwd(const CUtensorMap& own0, const CUtensorMap& own1, const CUtensorM
   const size_t smem = sizeof(BwdSmem<MODE>) + 1024;
   const int grid = N < sm_count() ? N : sm_count();
   long long* prof = g_bwd_prof;
+#define AMP_LAUNCH_BWD(NH_, PROF_, prof_)                                                                                          \
+  do {                                                                                                                           \
+    AMPCONV_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_bf16_kernel<HD, MODE, NH_, PROF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          (int)smem));                                                                           \
+    attn_bwd_bf16_kernel<HD, MODE, NH_, PROF_><<<grid, threads_of(MODE), smem, stream>>>(                                         \
+        own0, own1, oth0, oth1, rowptr, nbr, slot_of, order, lse2, delta, d_qkv, counter, status, N, F, s0, s1, out_ld, out_c0,   \
+        out_c1, halo_bf16, halo_from, prof_);                                                                                    \
+  } while (0)
   if (prof) {
-    AMPCONV_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_bf16_kernel<HD, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_bwd_bf16_kernel<HD, MODE, true><<<grid, threads_of(MODE), smem, stream>>>(own0, own1, oth0, oth1, rowptr, nbr, slot_of, order, lse2, delta,
-                                                                          d_qkv, counter, status, N, F, s0, s1, out_ld, out_c0, out_c1, halo_bf16, halo_from, prof);
+    if (F > 64) AMP_LAUNCH_BWD(2, true, prof);
+    else AMP_LAUNCH_BWD(1, true, prof);
   } else {
-    AMPCONV_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_bf16_kernel<HD, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_bwd_bf16_kernel<HD, MODE, false><<<grid, threads_of(MODE), smem, stream>>>(own0, own1, oth0, oth1, rowptr, nbr, slot_of, order, lse2, delta,
-                                                                           d_qkv, counter, status, N, F, s0, s1, out_ld, out_c0, out_c1, halo_bf16, halo_from, nullptr);
+    if (F > 64) AMP_LAUNCH_BWD(2, false, nullptr);
+    else AMP_LAUNCH_BWD(1, false, nullptr);
   }
+#undef AMP_LAUNCH_BWD
   AMPCONV_CHECK_LAUNCH();
   return AMPCONV_OK;
 }
