@@ -11,8 +11,13 @@
 //       operand ever waits for a row sum.  delta[p,h,i] is written for MODE_DKV.
 //   MODE_DKV (source-sorted): own tiles = K_s, V_s (per source), edge tiles = Q'_t, dO_t plus the
 //       lse2 / delta rows of the edge (bulk copies).  Everything is transposed (thread = source token):
-//       X = K_h Q_h^T, Y = V_h dO_h^T;  P^T = exp2(X - lse2_col), dS^T = P^T o (Y - delta_col);
+//       X = K_h Q_h^T - 1 lse2^T, Y = V_h dO_h^T - 1 delta^T;  P^T = exp2(X), dS^T = P^T o Y;
 //       dV_h += P^T dO_h,  dK_h += dS^T Q'_h, both accumulated in TMEM over the node's edges.
+//       The column statistics are subtracted BY THE TENSOR CORE: four statistics warps turn the edge's lse2 / delta rows
+//       into a bf16 tile S (row = destination token, head h at columns [16h, 16h+4) = -lse_hi, -lse_lo, -delta_hi,
+//       -delta_lo with x_hi = bf16(x), x_lo = bf16(x - x_hi): 16 mantissa bits) and every score MMA gets one more
+//       K = 16 step against a constant tile of ones (columns 0, 1 for X; 18, 19 for Y).  The elementwise warps are left
+//       with exp2, one multiply and the two bf16 packs per score element.
 //
 // Work split: a half-item = (edge, head, half) covers 64 of the 128 score columns.  Its two fp32 score tiles
 // X | Y (64 + 64 columns) live in one of three TMEM sets (columns [128 s, 128 s + 128)); columns [384, 512) hold
@@ -37,9 +42,10 @@ using namespace umma;
 constexpr int kD = 64;
 constexpr int kTileBytes = 128 * 128;
 constexpr int kEwWarps = 16;     // elementwise warps: 4 TMEM lane quarters x 4 column groups of 16 score columns
-constexpr int kFoldWarps = 4;    // MODE_DQ only: one warp per TMEM lane quarter folds delta o (P K) and writes dQ
-// elementwise warps + producer warp + score-MMA warp + 2 consumer-MMA warps (+ fold warps)
-__host__ __device__ constexpr int threads_of(int mode) { return (kEwWarps + 4 + (mode == 0 ? kFoldWarps : 0)) * 32; }
+constexpr int kFoldWarps = 4;    // MODE_DQ: one warp per TMEM lane quarter folds delta o (P K) and writes dQ;
+                                 // MODE_DKV: the same four warps build the edge's statistics tile (see below)
+// elementwise warps + producer warp + score-MMA warp + 2 consumer-MMA warps + fold / statistics warps
+__host__ __device__ constexpr int threads_of(int) { return (kEwWarps + 4 + kFoldWarps) * 32; }
 constexpr int kSets = 3;         // TMEM score sets of 128 columns
 constexpr int kAccCol = 384;     // accumulator block 0 at [384, 448), block 1 at [448, 512)
 constexpr int MODE_DQ = 0, MODE_DKV = 1;
@@ -66,9 +72,11 @@ struct BwdSmem {
   static constexpr int NS = 3;
   uint8_t own[2][2][kTileBytes];        // [slot][tile 0/1]
   uint8_t edge[NS][2][kTileBytes];      // [stage][tile 0/1]
+  uint8_t cst[MODE == MODE_DKV ? kTileBytes : 1024];         // MODE_DKV: constant selector tile (ones at columns 0,1 and 18,19)
+  uint8_t stile[2][MODE == MODE_DKV ? kTileBytes : 1024];    // MODE_DKV: statistics tile of the edge, double-buffered
   static constexpr int NSTAT = MODE == MODE_DKV ? 2 : 1;
   float stat[NS][NSTAT][kStatFloats];   // lse2 (both modes) / delta (MODE_DKV) rows of the edge, bulk-copied by the producer
-  float dl[8][4][128];                  // MODE_DQ: partial delta of [item & 7][group * 2 + column block][row]
+  float dl[MODE == MODE_DQ ? 8 : 1][4][128];   // MODE_DQ: partial delta of [item & 7][group * 2 + column block][row]
   float racc[MODE == MODE_DQ ? 64 * 128 : 4];   // MODE_DQ: - sum_e delta_e o (P_e K) of the node, [column][row]
   uint64_t own_full[2], own_empty[2];
   uint64_t edge_full[NS], edge_empty[NS];
@@ -76,6 +84,7 @@ struct BwdSmem {
   uint64_t acc_full, acc_empty;
   uint64_t dl_bar[8][4];                // MODE_DQ: [item & 7][lane quarter]: the quarter's four warps wrote their partial deltas
   uint64_t ko_full[4], ko_empty[4];     // MODE_DQ: ring of P K results (slot = item % (64 / HD))
+  uint64_t st_full[2], st_empty[2];     // MODE_DKV: statistics tile written / no longer read by the score MMAs
   NodeSlot slot[2];
   uint32_t tmem_base;
 };
@@ -140,7 +149,9 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sm.own_full[i], 1);
-      mbar_init(&sm.own_empty[i], 1 + kEwWarps + 2 + (MODE == MODE_DQ ? kFoldWarps : 0));
+      mbar_init(&sm.own_empty[i], 1 + kEwWarps + 2 + kFoldWarps);
+      mbar_init(&sm.st_full[i], kFoldWarps);
+      mbar_init(&sm.st_empty[i], 1);
     }
     for (int i = 0; i < kSets; ++i) {
       mbar_init(&sm.xy_full[i], 1);
@@ -149,7 +160,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
     }
     for (int i = 0; i < NS; ++i) {
       mbar_init(&sm.edge_full[i], 1);
-      mbar_init(&sm.edge_empty[i], 3 + kEwWarps);
+      mbar_init(&sm.edge_empty[i], 3 + (MODE == MODE_DQ ? kEwWarps : kFoldWarps));   // the readers of the statistics rows
     }
     for (int i = 0; i < 32; ++i) mbar_init(&sm.dl_bar[i >> 2][i & 3], 4);
     for (int i = 0; i < 4; ++i) {
@@ -159,6 +170,20 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
     mbar_init(&sm.acc_full, 2);
     mbar_init(&sm.acc_empty, MODE == MODE_DQ ? kFoldWarps : kEwWarps);
     fence_barrier_init();
+  }
+  if (MODE == MODE_DKV) {
+    // selector tile: row r, 16-byte chunk 0 = (1, 1, 0, ...), chunk 2 = (0, 0, 1, 1, 0, ...) (128B swizzle: chunk c of row r
+    // sits at chunk position c ^ (r & 7)); statistics tiles start as zeros, only the even chunks are ever rewritten
+    for (int i = threadIdx.x; i < kTileBytes / 16; i += blockDim.x) {
+      const int r = i >> 3, c = (i & 7) ^ (r & 7);
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (c == 0) v.x = 0x3f803f80u;      // bf16 1.0 | 1.0
+      if (c == 2) v.y = 0x3f803f80u;
+      reinterpret_cast<uint4*>(sm.cst)[i] = v;
+      reinterpret_cast<uint4*>(sm.stile[0])[i] = make_uint4(0u, 0u, 0u, 0u);
+      reinterpret_cast<uint4*>(sm.stile[1])[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async_smem();
   }
   if (warp == kEwWarps && lane == 0) {
     prefetch_tensormap(&own0);
@@ -265,6 +290,8 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
         for (int e = ns.e_begin; e < ns.e_end; ++e, ++edge) {
           const uint32_t st = edge % NS;
           AMP_WAIT(&sm.edge_full[st], (edge / NS) & 1, 202);
+          const uint32_t sb = edge & 1;
+          if (MODE == MODE_DKV) AMP_WAIT(&sm.st_full[sb], (edge >> 1) & 1, 204);   // the edge's statistics tile is written
 #pragma unroll
           for (int h = 0; h < H; ++h) {
             for (int half = 0; half < nhalf; ++half, ++k) {
@@ -283,10 +310,18 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
 #pragma unroll
               for (int ks = 0; ks < HD / 16; ++ks)
                 mma_ss_w(tmem + set * 128 + 64, desc_advance(a1, ks * 32), desc_advance(b1, ks * 32), idesc_xy, ks > 0);
+              if (MODE == MODE_DKV) {
+                // one more K step each: X -= 1 lse2^T, Y -= 1 delta^T (selector tile x the edge's statistics tile, head slice h)
+                const uint64_t ac = smem_desc(smem_u32(sm.cst), 16, 1024, LAYOUT_SW128);
+                const uint64_t bs = smem_desc(smem_u32(sm.stile[sb]) + half * 8192 + h * 32, 16, 1024, LAYOUT_SW128);
+                mma_ss_w(tmem + set * 128, ac, bs, idesc_xy, 1u);
+                mma_ss_w(tmem + set * 128 + 64, desc_advance(ac, 32), bs, idesc_xy, 1u);
+              }
               mma_commit_w(&sm.xy_full[set]);
             }
           }
           mma_commit_w(&sm.edge_empty[st]);
+          if (MODE == MODE_DKV) mma_commit_w(&sm.st_empty[sb]);
           if (e + 1 == ns.e_end) mma_commit_w(&sm.own_empty[qb]);
         }
       }
@@ -441,10 +476,57 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
         pr[7] = item;
       }
     }
+  } else if (MODE == MODE_DKV && warp >= kEwWarps + 4) {
+    // ------------------------------------------------------------------ statistics warps (MODE_DKV): thread = destination token
+    //   per edge: the bulk-copied fp32 rows lse2[h][i], delta[h][i] become the bf16 tile S[i][16h .. 16h+3] =
+    //   (-lse_hi, -lse_lo, -delta_hi, -delta_lo); rows >= F and the odd 16-byte chunks stay zero.
+    // register pool of the CTA: 768 threads x 80 at launch; the elementwise warps take 16 x 32 x (96 - 80) = 8192, which the
+    // control warps (80 -> 48) and these warps (80 -> 48) release: 2 x 128 x 32 = 8192 (setmaxnreg.inc blocks until then)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    {
+      const int row = (warp & 3) * 32 + lane;
+      const bool row_ok = row < F;
+      uint32_t qi = 0, edge = 0;
+      for (;; ++qi) {
+        const uint32_t qb = qi & 1;
+        AMP_WAIT_A(SM_OFF(own_full) + 8 * qb, (qi >> 1) & 1, 501);
+        const NodeSlot ns = uniform_slot(sm.slot[qb]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_a(SM_OFF(own_empty) + 8 * qb);
+        if (ns.node < 0) break;
+        for (int e = ns.e_begin; e < ns.e_end; ++e, ++edge) {
+          const uint32_t st = edge % NS, sb = edge & 1;
+          AMP_WAIT_A(SM_OFF(edge_full) + 8 * st, (edge / NS) & 1, 502);
+          AMP_WAIT_A(SM_OFF(st_empty) + 8 * sb, ((edge >> 1) & 1) ^ 1, 503);
+          if (row_ok) {
+            const uint32_t src = SM_OFF(stat) + (uint32_t)(st * 2 * kStatFloats * 4) + 4 * row;
+            const uint32_t dst = SM_OFF(stile) + sb * kTileBytes + row * 128;
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+              const float l = -lds_f32(src + h * Fs * 4);
+              const float dd = -lds_f32(src + kStatFloats * 4 + h * Fs * 4);
+              // x = hi + lo with hi = bf16(x), lo = bf16(x - hi)
+              const uint32_t lh = pack_bf16x2(l, 0.f) & 0xffffu, dh = pack_bf16x2(dd, 0.f) & 0xffffu;
+              const float l_lo = l - __uint_as_float(lh << 16), d_lo = dd - __uint_as_float(dh << 16);
+              const uint32_t w0 = lh | (pack_bf16x2(0.f, l_lo) & 0xffff0000u);
+              const uint32_t w1 = dh | (pack_bf16x2(0.f, d_lo) & 0xffff0000u);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (((2 * h) ^ (row & 7)) << 4)), "r"(w0), "r"(w1),
+                           "r"(0u), "r"(0u)
+                           : "memory");
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive_a(SM_OFF(st_full) + 8 * sb);
+            mbar_arrive_a(SM_OFF(edge_empty) + 8 * st);
+          }
+        }
+      }
+    }
   } else {
     // ------------------------------------------------------------------ elementwise warps
-    if (MODE == MODE_DQ) asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
-    else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
     const uint32_t q4 = warp & 3;                   // TMEM lane quarter
     const uint32_t grp = warp >> 3;                 // group: works on half-items with k & 1 == grp
     const uint32_t cb = (warp >> 2) & 1;            // column block: score columns [32cb, 32cb+32) of the half
@@ -477,12 +559,11 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       if (ns.node < 0) break;
       for (int e = ns.e_begin; e < ns.e_end; ++e, ++ei) {
         const uint32_t st = ei % NS;
-        AMP_TWAIT(1, SM_OFF(edge_full) + 8 * st, (ei / NS) & 1, 306);   // acquire the bulk-copied statistics rows
+        if (MODE == MODE_DQ) AMP_TWAIT(1, SM_OFF(edge_full) + 8 * st, (ei / NS) & 1, 306);   // acquire the bulk-copied statistics rows
         // NOT unrolled: one copy of the body keeps the elementwise loop inside the instruction cache
 #pragma unroll 1
         for (int h = 0; h < H; ++h, ++item) {
           const uint32_t ls_addr = SM_OFF(stat) + (uint32_t)((st * Smem::NSTAT * kStatFloats + h * Fs) * 4);
-          const uint32_t ds_addr = ls_addr + kStatFloats * 4;
           // MODE_DQ: this thread's row statistic (rows >= F read stale shared memory: they only reach discarded output rows)
           const float L = MODE == MODE_DQ ? lds_f32(ls_addr + 4 * row) : 0.f;
           float2 dl2 = make_float2(0.f, 0.f);
@@ -509,21 +590,20 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
               if (ch == 0) tmem_ld_wait();
               // one pair of score columns; TAIL adds the selects that keep columns >= F (zero-filled tile rows, undefined
               // statistics) out of delta and out of the MMA operands
-              auto pair = [&](int j, float2 l2, float2 d2, auto tail_tag) {
+              auto pair = [&](int j, auto tail_tag) {
                 constexpr bool TAIL = decltype(tail_tag)::value;
                 const int c0 = col0 + 2 * j;
                 const float2 x2 = make_float2(__uint_as_float(xs[ch][2 * j]), __uint_as_float(xs[ch][2 * j + 1]));
                 const float2 y2 = make_float2(__uint_as_float(ys[ch][2 * j]), __uint_as_float(ys[ch][2 * j + 1]));
-                float2 p2, u2;
+                float2 p2;
                 if (MODE == MODE_DQ) {
                   const float2 e2 = f2add(x2, make_float2(-L, -L));
                   p2 = make_float2(ex2_approx(e2.x), ex2_approx(e2.y));
-                  u2 = f2mul(p2, y2);
                 } else {
-                  const float2 e2 = f2add(x2, make_float2(-l2.x, -l2.y));
-                  p2 = make_float2(ex2_approx(e2.x), ex2_approx(e2.y));
-                  u2 = f2mul(p2, f2add(y2, make_float2(-d2.x, -d2.y)));
+                  // the column statistics were subtracted by the score MMAs (statistics tile)
+                  p2 = make_float2(ex2_approx(x2.x), ex2_approx(x2.y));
                 }
+                float2 u2 = f2mul(p2, y2);
                 if (TAIL) {
                   if (c0 >= F) { p2.x = 0.f; u2.x = 0.f; }
                   if (c0 + 1 >= F) { p2.y = 0.f; u2.y = 0.f; }
@@ -532,22 +612,12 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
                 px[j] = pack_bf16x2(p2.x, p2.y);
                 py[j] = pack_bf16x2(u2.x, u2.y);
               };
-              // four pairs of column statistics per shared-memory vector load (MODE_DKV)
-              auto quad = [&](int v4, auto tail_tag) {
-                float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a4;
-                if (MODE == MODE_DKV) {
-                  a4 = lds_f4(ls_addr + (col0 + 4 * v4) * 4);
-                  b4 = lds_f4(ds_addr + (col0 + 4 * v4) * 4);
-                }
-                pair(2 * v4, make_float2(a4.x, a4.y), make_float2(b4.x, b4.y), tail_tag);
-                pair(2 * v4 + 1, make_float2(a4.z, a4.w), make_float2(b4.z, b4.w), tail_tag);
-              };
               if (col0 + 16 > F) {     // warp-uniform: only the chunk that straddles F and the ones behind it
 #pragma unroll
-                for (int v4 = 0; v4 < 4; ++v4) quad(v4, TrueTag{});
+                for (int j = 0; j < 8; ++j) pair(j, TrueTag{});
               } else {
 #pragma unroll
-                for (int v4 = 0; v4 < 4; ++v4) quad(v4, FalseTag{});
+                for (int j = 0; j < 8; ++j) pair(j, FalseTag{});
               }
               // packed operands go to the first 8 of the chunk's own 16 columns: always behind this thread's own reads
               tmem_st_32x32b_x8(xbase + 16 * ch, px);
@@ -568,8 +638,10 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
             AMP_PHASE(3);
           }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive_a(SM_OFF(edge_empty) + 8 * st);   // this warp no longer reads the stage's statistics rows
+        if (MODE == MODE_DQ) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive_a(SM_OFF(edge_empty) + 8 * st);   // this warp no longer reads the stage's statistics rows
+        }
       }
       // node epilogue.  MODE_DQ: the fold warps own the accumulators (they add the delta term and write dQ); the
       // elementwise warps go straight on to the next node.
