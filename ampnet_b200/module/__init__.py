@@ -1,4 +1,5 @@
-"""Callers of the hot path: the reference's 2-layer model around ``AMPConv``."""
+"""Callers of the hot path: the reference's models around ``AMPConv``."""
 from .amp_gcn import AMPGCN, dropout_adj
+from .amp_net_classifier import AMPNetClassifier
 
-__all__ = ["AMPGCN", "dropout_adj"]
+__all__ = ["AMPGCN", "AMPNetClassifier", "dropout_adj"]

@@ -37,7 +37,7 @@ def load_message_passing_kat():
     return mod
 
 
-def load_amp_gcn_module():
+def load_amp_gcn_module(which="gcn"):
     """The reference's 2-layer model ``src/ampnet/module/amp_gcn.py`` (``AMPGCN``), loaded by path, unmodified
     (SURVEY.md Appendix A step 3): plotting libraries are mocked, ``torch_geometric.datasets.Planetoid`` and
     ``torch_geometric.utils.dropout.dropout_adj`` are stand-ins (``dropout_adj`` is the identity for p = 0 or eval, the only
@@ -81,4 +81,12 @@ def load_amp_gcn_module():
 
     load("src.ampnet.conv.amp_conv", os.path.join("conv", "amp_conv.py"))
     load("src.ampnet.utils.utils", os.path.join("utils", "utils.py"))
+    if which == "classifier":
+        return load("src.ampnet.module.amp_net_classifier_Rahul", os.path.join("module", "amp_net_classifier_Rahul.py"))
     return load("src.ampnet.module.amp_gcn", os.path.join("module", "amp_gcn.py"))
+
+
+def load_amp_net_classifier_module():
+    """The reference's ``AMPNetClassifier`` (``src/ampnet/module/amp_net_classifier_Rahul.py``), loaded by path, unmodified,
+    through the same package scaffolding as ``load_amp_gcn_module``."""
+    return load_amp_gcn_module(which="classifier")

@@ -16,9 +16,9 @@ def pytest_configure(config):
 
 
 def golden_names():
-    """Per-layer (AMPConv) goldens; the model-level `ampgcn_*` files have their own schema and tests."""
+    """Per-layer (AMPConv) goldens; the model-level `ampgcn_*` / `ampnetclf_*` files have their own schema and tests."""
     return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR)
-                  if f.endswith(".npz") and not f.startswith("ampgcn_"))
+                  if f.endswith(".npz") and not f.startswith(("ampgcn_", "ampnetclf_")))
 
 
 def load_golden(name):

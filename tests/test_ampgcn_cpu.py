@@ -61,3 +61,20 @@ def test_dropout_adj_semantics():
     assert 0.65 < kept.size(1) / 10000 < 0.75
     with pytest.raises(ValueError):
         dropout_adj(ei, p=1.5)
+
+
+@pytest.mark.parametrize("name", ["ampnetclf_small", "ampnetclf_d64"])
+def test_reference_classifier_state_dict_loads_strictly(name):
+    """AMPNetClassifier mirror: same parameter names and shapes as the reference class
+    (amp_net_classifier_Rahul.py:7-43), pinned by the state_dict the reference's own model produced."""
+    from ampnet_b200 import AMPNetClassifier
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    n, e, f, d, h, classes = [int(v) for v in g["config"]]
+    model = AMPNetClassifier(num_heads=h, embed_dim=d, n_original_features=f, out_dim=classes)
+    state = {k[len("param/"):]: torch.from_numpy(g[k]).float() for k in g.files if k.startswith("param/")}
+    assert sorted(state) == sorted(model.state_dict().keys())
+    model.load_state_dict(state, strict=True)
+    with pytest.raises((TypeError, RuntimeError, ImportError)):
+        # CPU tensors: the layers have no CPU path
+        from types import SimpleNamespace
+        model(SimpleNamespace(x=torch.zeros(n, f * d), edge_index=torch.zeros(2, 1, dtype=torch.long)))
