@@ -347,6 +347,24 @@ __device__ __forceinline__ uint32_t ex2_bf16x2(uint32_t x) {
 __device__ __forceinline__ float2 f2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
 __device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
 __device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+// exp2 of a pair WITHOUT the MUFU pipe (the binding pipe of the attention kernels): Cody-Waite split through the
+// 1.5 * 2^23 magic constant (round to nearest integer n, f = x - n in [-0.5, 0.5]), degree-3 polynomial for 2^f (max
+// relative error 7.5e-5, far below the bf16 rounding of the probabilities it feeds), exponent inserted with one shift-add
+// per element.  3 FADD2/FFMA2 + 3 FFMA2 packed, 2 FMNMX + 2 shift-adds scalar = 5 issue slots per element on the FMA / ALU
+// pipes against 1 slot + 8 pipe cycles of MUFU.EX2.  Inputs are clamped to >= -125 (2^-125 is normal: no exponent wrap);
+// -inf (masked score columns) therefore yields 2^-125 ~ 2e-38, which vanishes in every sum it enters.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -125.f);
+  x.y = fmaxf(x.y, -125.f);
+  const float2 t = f2add(x, make_float2(12582912.f, 12582912.f));        // low mantissa bits = round(x) (two's complement)
+  const float2 n = f2add(t, make_float2(-12582912.f, -12582912.f));
+  const float2 f = f2fma(n, make_float2(-1.f, -1.f), x);
+  float2 q = f2fma(f, make_float2(0.0551716685f, 0.0551716685f), make_float2(0.2426111251f, 0.2426111251f));
+  q = f2fma(q, f, make_float2(0.6932609677f, 0.6932609677f));
+  q = f2fma(q, f, make_float2(0.9999280572f, 0.9999280572f));
+  return make_float2(__int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23)),
+                     __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23)));
+}
 __device__ __forceinline__ float4 lds_f4(uint32_t smem_addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_addr));
