@@ -326,8 +326,9 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": pk["source"], "kernel_ms": kern_ms, "algorithmic_bytes": alg,
-                "mufu_frac": {"note": "fraction of the exp2 issue peak (16 per clk per SM at 1.965 GHz, 148 SMs); "
-                                      "the binding pipe of all three kernels at head_dim 16", **mufu}}
+                "mufu_frac": {"note": "exponentials per second relative to the MUFU exp2 issue peak (16 per clk per SM at 1.965 GHz, "
+                                      "148 SMs), the binding pipe of all three kernels at head_dim 16; the forward evaluates "
+                                      "a quarter of its exponentials on the FMA pipe instead", **mufu}}
 
     if rank != 0:
         return
