@@ -319,6 +319,14 @@ def dist_amp_conv(x_local, pg, w_in, b_in, w_out, b_out, num_heads, group=None):
     """AMPConv forward for the rows this rank owns (x_local = x[lo:hi]); differentiable; bf16 (tcgen05) family only."""
     d = w_in.shape[1]
     f = x_local.shape[1] // d
-    if not F_.bf16_supported(f, d, num_heads):
-        raise ValueError("the partitioned path uses the tcgen05 family: embed_dim 64, head_dim 16 or 32, F <= 128")
-    return _DistAMPConvFunction.apply(x_local.contiguous(), w_in, b_in, w_out, b_out, pg, num_heads, group)
+    if F_.bf16_supported(f, d, num_heads):
+        return _DistAMPConvFunction.apply(x_local.contiguous(), w_in, b_in, w_out, b_out, pg, num_heads, group)
+    if F_.bf16_grouped_supported(f, d, num_heads):
+        # head_dim 8 (the ogbn-products shape): two 4-head passes over zero-padded heads, composed by autograd
+        # (functional.hd8_compose; the algebra is pinned on the CPU by tests/test_hd8_grouping_cpu.py, the partitioned
+        # composition itself has not run on hardware yet -- DESIGN.md section 6)
+        def layer(x_, wi, bi, wo, bo, heads):
+            return _DistAMPConvFunction.apply(x_.contiguous(), wi.contiguous(), bi.contiguous(), wo.contiguous(),
+                                              bo.contiguous(), pg, heads, group)
+        return F_.hd8_compose(layer, x_local, w_in, b_in, w_out, b_out)
+    raise ValueError("the partitioned path uses the tcgen05 family: embed_dim 64, head_dim 8, 16 or 32, F <= 128")

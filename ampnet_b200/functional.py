@@ -225,6 +225,21 @@ def hd8_compact(per_group, sections):
     return torch.stack(parts, dim=2).reshape(rows, sections * 64)
 
 
+def hd8_compose(layer_fn, x, w_in, b_in, w_out, b_out):
+    """The same decomposition at the autograd level: ``layer_fn(x, w_in, b_in, w_out, b_out, num_heads)`` is any differentiable
+    embed-64 AMPConv layer; the 8-head layer is the sum of two 4-head calls with zero-padded parameters (built with
+    differentiable tensor ops, so un-padding the parameter gradients is autograd's job).  The inner layer scales its
+    scores by 1/sqrt(16): the padded query rows carry the missing sqrt(2); out_proj's bias goes to the first call only.
+    Used where the layer body is not the single-GPU one (``distributed.dist_amp_conv``); costs the node-level kernels twice."""
+    out = None
+    q_scale = torch.cat([w_in.new_full((64,), 2.0 ** 0.5), w_in.new_ones(128)])
+    for g in range(2):
+        w_in_g, b_in_g, w_out_g = hd8_group_params(w_in, b_in, w_out, g)
+        o = layer_fn(x, w_in_g * q_scale[:, None], b_in_g * q_scale, w_out_g, b_out if g == 0 else torch.zeros_like(b_out), 4)
+        out = o if out is None else out + o
+    return out
+
+
 def _forward_bf16_hd8(x, graph, w_in, b_in, w_out, b_out, num_heads):
     n, width = x.shape
     d = w_in.shape[1]

@@ -81,3 +81,38 @@ def test_padded_columns_stay_zero():
         real = torch.arange(64).view(4, 16)[:, :8].reshape(-1)
         assert torch.equal(w_out_g[:, real], w_out[:, 32 * g:32 * g + 32])
         assert torch.equal(w_in_g[128 + real], w_in[128 + 32 * g:128 + 32 * g + 32])
+
+
+def _torch_layer(x, ei, w_in, b_in, w_out, b_out, h):
+    """Differentiable float64 restatement of the layer (amp_conv.py:24-51 with stock MHA arithmetic), any head count."""
+    n = x.shape[0]
+    d = w_in.shape[1]
+    f = x.shape[1] // d
+    hd = d // h
+    e = ei.shape[1]
+    qkv = x.view(n, f, d) @ w_in.T + b_in
+    q, k, v = qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:]
+    qe = q[ei[1]].view(e, f, h, hd).transpose(1, 2)
+    ke = k[ei[0]].view(e, f, h, hd).transpose(1, 2)
+    ve = v[ei[0]].view(e, f, h, hd).transpose(1, 2)
+    p = torch.softmax(qe @ ke.transpose(-1, -2) / hd ** 0.5, dim=-1)
+    o = (p @ ve).transpose(1, 2).reshape(e, f, d) @ w_out.T + b_out
+    deg = torch.bincount(ei[1], minlength=n).clamp(min=1).double()
+    return (torch.zeros(n, f, d, dtype=x.dtype).index_add_(0, ei[1], o) / deg[:, None, None]).reshape(n, f * d)
+
+
+def test_autograd_level_composition_equals_the_eight_head_layer():
+    """functional.hd8_compose (used by the partitioned path): out, dX and all four parameter gradients."""
+    from ampnet_b200.functional import hd8_compose
+    n, e, f, d, h = 7, 20, 4, 64, 8
+    x, ei, p, d_out = cases.make_inputs(n, e, f, d, h, graph="skewed", seed=4)
+    ref = numpy_oracle.backward(x, ei, p["in_proj_weight"], p["in_proj_bias"], p["out_proj_weight"], p["out_proj_bias"], h, d_out)
+    t = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float64)).requires_grad_(True)
+    xt, w_in, b_in, w_out, b_out = t(x), t(p["in_proj_weight"]), t(p["in_proj_bias"]), t(p["out_proj_weight"]), t(p["out_proj_bias"])
+    eit = torch.from_numpy(ei)
+    out = hd8_compose(lambda x_, wi, bi, wo, bo, heads: _torch_layer(x_, eit, wi, bi, wo, bo, heads), xt, w_in, b_in, w_out, b_out)
+    (out * torch.from_numpy(d_out).double()).sum().backward()
+    assert np.abs(out.detach().numpy() - ref["out"]).max() < 1e-10
+    assert np.abs(xt.grad.numpy() - ref["d_x"]).max() < 1e-10
+    for got, key in ((w_in, "d_in_proj_weight"), (b_in, "d_in_proj_bias"), (w_out, "d_out_proj_weight"), (b_out, "d_out_proj_bias")):
+        assert np.abs(got.grad.numpy() - ref[key]).max() < 1e-9, key
