@@ -152,7 +152,8 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {spec['desc']} (N={spec['n']}, E={spec['e']}, F={spec['f']}, "
-                               f"d={spec['d']}, H={spec['h']})", "graph": "uniform", "sample": sample},
+                               f"d={spec['d']}, H={spec['h']}), one AMPConv layer fwd+bwd, {args.graph} graph seed 7",
+                   "mode": "fp32 (the reference's eager op chain on the host cores)", "sample": sample},
         "cpu_baseline": {"value": value, "unit": "edges/s", "cores": r["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
