@@ -150,7 +150,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {spec['desc']} (N={spec['n']}, E={spec['e']}, F={spec['f']}, "
                                f"d={spec['d']}, H={spec['h']}), one AMPConv layer fwd+bwd, {args.graph} graph seed 7",
                    "mode": "fp32 (the reference's eager op chain on the host cores)", "sample": sample},
@@ -343,12 +343,12 @@ def run_ours(args):
                          f"reference op chain (oracle/torch_port.py), edge-chunked by {r['chunk']}"}
     line = {
         "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32" if args.mode == "fp32" else "bf16", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {spec['desc']} (N={n}, E={e}, F={f}, d={d}, H={h}), one AMPConv layer "
                                f"fwd+bwd, {args.graph} graph seed 7", "mode": args.mode,
                    "l2": "inputs larger than L2 (x = %.1f GB); no flush" % (n * f * d * 4 / 1e9),
-                   "parallelism": "1 GPU" if world == 1 else f"{world} independent graph shards (weak scaling)"},
+                   "parallelism": "1 GPU (bench.py --gpus N partitions this same graph over N GPUs: strong scaling)"},
         "node_updates_per_s": world * n / (ms_step * 1e-3),
         "clocks": clocks.summary(),
         "e2e": {"value": world * e / (e2e_ms * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": h2d,
