@@ -62,3 +62,22 @@ def test_errors_are_loud_and_there_is_no_cpu_path():
         conv(torch.zeros(5, 8), ei)          # CPU tensor: no fallback
     with pytest.raises(AssertionError):   # same assertion as the reference's MHA (custom_multihead_attn.py:58-59)
         AMPConv(6, 4)
+
+
+def test_mode_resolution_per_baseline_config():
+    """Which kernel family serves which BASELINE config (host logic + the library's pure-C support predicate; no GPU)."""
+    from ampnet_b200 import functional as F_
+    assert F_.resolve_mode("auto", 128, 64, 4) == "bf16"        # C4: ogbn-arxiv token shape, head_dim 16
+    assert F_.resolve_mode("bf16", 20, 64, 2) == "bf16"         # head_dim 32
+    assert F_.resolve_mode("auto", 100, 64, 8) == "bf16g"       # C5: ogbn-products token shape, head-group decomposition
+    assert F_.resolve_mode("bf16", 100, 64, 8) == "bf16g"
+    assert F_.resolve_mode("fp32", 100, 64, 8) == "fp32"        # the strict family is always available
+    assert F_.resolve_mode("auto", 20, 128, 4) == "fp32"        # C2: embed 128 is outside the tensor-core family
+    assert F_.resolve_mode("auto", 1433, 12, 3) == "fp32"       # C1
+    assert F_.resolve_mode("auto", 2, 3, 1) == "fp32"           # C3
+    assert F_.resolve_mode("auto", 129, 64, 4) == "fp32"        # more than 128 tokens per node
+    for f, d, h in ((20, 128, 4), (129, 64, 8), (100, 64, 16)):
+        with pytest.raises(ValueError):
+            F_.resolve_mode("bf16", f, d, h)
+    with pytest.raises(ValueError):
+        F_.resolve_mode("tf32", 128, 64, 4)
