@@ -50,6 +50,10 @@ constexpr int kSets = 3;         // TMEM score sets of 128 columns
 constexpr int kAccCol = 384;     // accumulator block 0 at [384, 448), block 1 at [448, 512)
 constexpr int MODE_DQ = 0, MODE_DKV = 1;
 constexpr int kStatFloats = 4 * 128;   // H * roundup4(F) <= 512 floats per edge and statistic
+// Share of the exponentials evaluated on the FMA pipe (umma.cuh: ex2_poly2) instead of MUFU: every fourth pair of score
+// columns when enabled.  The forward gained 4 % from it; in these passes it is NOT measured yet, so the
+// switches stay off and the compiled kernels are unchanged.
+constexpr bool kPolyShareDq = false, kPolyShareDkv = false;
 
 struct NodeSlot {
   int node, e_begin, e_end;
@@ -596,12 +600,13 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
                 const float2 x2 = make_float2(__uint_as_float(xs[ch][2 * j]), __uint_as_float(xs[ch][2 * j + 1]));
                 const float2 y2 = make_float2(__uint_as_float(ys[ch][2 * j]), __uint_as_float(ys[ch][2 * j + 1]));
                 float2 p2;
+                const bool poly = (MODE == MODE_DQ ? kPolyShareDq : kPolyShareDkv) && (j & 3) == 3;
                 if (MODE == MODE_DQ) {
                   const float2 e2 = f2add(x2, make_float2(-L, -L));
-                  p2 = make_float2(ex2_approx(e2.x), ex2_approx(e2.y));
+                  p2 = poly ? ex2_poly2(e2) : make_float2(ex2_approx(e2.x), ex2_approx(e2.y));
                 } else {
                   // the column statistics were subtracted by the score MMAs (statistics tile)
-                  p2 = make_float2(ex2_approx(x2.x), ex2_approx(x2.y));
+                  p2 = poly ? ex2_poly2(x2) : make_float2(ex2_approx(x2.x), ex2_approx(x2.y));
                 }
                 float2 u2 = f2mul(p2, y2);
                 if (TAIL) {
