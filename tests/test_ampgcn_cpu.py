@@ -78,3 +78,26 @@ def test_reference_classifier_state_dict_loads_strictly(name):
         # CPU tensors: the layers have no CPU path
         from types import SimpleNamespace
         model(SimpleNamespace(x=torch.zeros(n, f * d), edge_index=torch.zeros(2, 1, dtype=torch.long)))
+
+
+def test_classifier_glue_with_stand_in_layers():
+    """The glue around the two layers (dropout off in eval, ELU after each layer, read-out, log-softmax, embeddings kept),
+    with the CUDA layers replaced by CPU stand-ins: amp_net_classifier_Rahul.py:45-57."""
+    from types import SimpleNamespace
+    from ampnet_b200 import AMPNetClassifier
+    torch.manual_seed(0)
+    model = AMPNetClassifier(num_heads=2, embed_dim=4, n_original_features=3, out_dim=5).eval()
+    assert [k for k, _ in model.named_children()] == ["layer_norm", "conv1", "post_conv_linear1", "conv2", "post_conv_linear2",
+                                                      "linear_out"]
+    model.conv1.forward = lambda x, ei: x * 2.0 - 1.0
+    model.conv2.forward = lambda x, ei: x.flip(1) + 0.5
+    x = torch.randn(7, 12)
+    out = model(SimpleNamespace(x=x, edge_index=torch.zeros(2, 1, dtype=torch.long)))
+    e1 = x * 2.0 - 1.0
+    e2 = torch.nn.functional.elu(e1).flip(1) + 0.5
+    ref = torch.log_softmax(model.linear_out(torch.nn.functional.elu(e2)), dim=1)
+    assert torch.allclose(out, ref) and torch.equal(model.conv1_embedding, e1) and torch.equal(model.conv2_embedding, e2)
+    model.train()
+    torch.manual_seed(1)
+    a = model(SimpleNamespace(x=x, edge_index=torch.zeros(2, 1, dtype=torch.long)))
+    assert not torch.allclose(a, ref)                      # dropout(0.6) is live in training mode
