@@ -12,7 +12,11 @@ Differences that are deliberate supersets of the reference's behaviour:
 * a width that is not a multiple of ``embed_dim`` raises ``ValueError`` (the reference prints
   "Error, invalid configuration" and then fails inside ``reshape``; ``amp_conv.py:32-36``);
 * the two side outputs are computed lazily on first read instead of on every forward (at the
-  ogbn-arxiv shape ``attn_output_weights`` alone would be 76 GB).
+  ogbn-arxiv shape ``attn_output_weights`` alone would be 76 GB); ``attention_weights(edge_ids)`` returns them for a
+  slice of edges, which is how a caller walks all of them in chunks;
+* ``mode``: "auto" (default) runs the tcgen05 bf16 family where it covers the shape (2e-2 bar of BASELINE.json) and the
+  strict fp32 family elsewhere; ``mode="fp32"`` forces the strict family (1e-4 bar), ``mode="bf16"`` raises where the
+  tensor-core family does not apply.
 """
 import torch
 import torch.nn as nn
@@ -22,7 +26,7 @@ from ..graph import get_graph
 
 
 class AMPConv(nn.Module):
-    def __init__(self, embed_dim, num_heads, mode="fp32"):
+    def __init__(self, embed_dim, num_heads, mode="auto"):
         super().__init__()
         self._holder = {}
         self._attn_output_weights = None
@@ -56,6 +60,18 @@ class AMPConv(nn.Module):
     @attn_output_weights.setter
     def attn_output_weights(self, value):
         self._attn_output_weights = value
+
+    def attention_weights(self, edge_ids=None):
+        """``attn_output_weights`` of the last forward for a slice of edges ([len(edge_ids), F, F], original edge ids), or all
+        of them.  The chunked reader for graphs where [E, F, F] does not fit (``attention_weights_chunks`` iterates)."""
+        if "saved" not in self._holder:
+            return None
+        return F_.attention_weights(self._holder["saved"], edge_ids)
+
+    def attention_weights_chunks(self, chunk_edges=4096):
+        if "saved" not in self._holder:
+            return iter(())
+        return F_.attention_weights_chunks(self._holder["saved"], chunk_edges)
 
     @property
     def attn_output(self):

@@ -417,7 +417,7 @@ static int attn_fwd_bf16_impl(const void* q, const void* k, const void* v,
     return AMPCONV_ERR_CUDA;
   int* counter = reinterpret_cast<int*>(workspace);
   int* status = counter + 1;
-  AMPCONV_CUDA_TRY(cudaMemsetAsync(counter, 0, 2 * sizeof(int), stream));
+  AMPCONV_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(int), stream));   // the status word (counter + 1) is the caller's: zeroed once per layer call
   const size_t smem = sizeof(FwdSmem) + 1024;
   const int grid = (int)(N < sm_count() ? N : sm_count());
   const int hd = d / H;

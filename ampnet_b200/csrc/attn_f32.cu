@@ -323,13 +323,14 @@ attn_bwd_dkv_f32_kernel(const float* __restrict__ qkv, const float* __restrict__
 __global__ void __launch_bounds__(256)
 attn_weights_f32_kernel(const float* __restrict__ qkv, const float* __restrict__ lse,
                         const int32_t* __restrict__ slot_dst, const int32_t* __restrict__ dst_src,
-                        const int32_t* __restrict__ dst_eid, float* __restrict__ weights,
-                        int F, int d, int H, float scale) {
+                        const int32_t* __restrict__ dst_eid, const int32_t* __restrict__ slots,
+                        float* __restrict__ weights, int F, int d, int H, float scale) {
   extern __shared__ __align__(16) float smem[];
   const int hd = d / H;
   float* Qs = smem;                       // [16][hd+1]
   float* Ks = smem + 16 * (hd + 1);       // [16][hd+1]
-  const int64_t p = blockIdx.x;
+  // all slots (output row = original edge id) or the listed ones (output row = position in the list)
+  const int64_t p = slots ? slots[blockIdx.x] : blockIdx.x;
   const int tiles = (F + 15) / 16;
   const int i0 = (blockIdx.y / tiles) * 16, j0 = (blockIdx.y % tiles) * 16;
   const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
@@ -351,7 +352,7 @@ attn_weights_f32_kernel(const float* __restrict__ qkv, const float* __restrict__
     }
   }
   if (i0 + ti < F && j0 + tj < F)
-    weights[((int64_t)dst_eid[p] * F + i0 + ti) * F + j0 + tj] = w / (float)H;
+    weights[((int64_t)(slots ? (int64_t)blockIdx.x : (int64_t)dst_eid[p]) * F + i0 + ti) * F + j0 + tj] = w / (float)H;
 }
 
 // slot -> destination node, recovered from the row pointer (one thread per node).
@@ -502,11 +503,29 @@ extern "C" int ampconv_attn_weights_f32(const float* qkv, const float* lse, cons
   const int tiles = (F + 15) / 16;
   dim3 grid((unsigned)E, (unsigned)(tiles * tiles));
   size_t smem = (size_t)2 * 16 * (hd + 1) * sizeof(float);
-  attn_weights_f32_kernel<<<grid, 256, smem, stream>>>(qkv, lse, slot_dst, dst_src, dst_eid, weights, F, d, H,
+  attn_weights_f32_kernel<<<grid, 256, smem, stream>>>(qkv, lse, slot_dst, dst_src, dst_eid, nullptr, weights, F, d, H,
                                                       1.0f / sqrtf((float)hd));
   cudaError_t le = cudaGetLastError();
   cudaFreeAsync(slot_dst, stream);
   if (le != cudaSuccess) return cuda_fail(le);
+  return AMPCONV_OK;
+}
+
+// Chunked form of the same side output: weights[m, i, j] for the M listed destination-sorted slots (slot_dst = the
+// destination node of EVERY slot, [E]); the caller walks the edge set in slices instead of holding [E, F, F].
+extern "C" int ampconv_attn_weights_slots_f32(const float* qkv, const float* lse, const int32_t* slot_dst,
+                                              const int32_t* dst_src, const int32_t* slots, int64_t M, float* weights,
+                                              int F, int d, int H, void* stream_) {
+  AMPCONV_REQUIRE(M >= 0 && F > 0 && d > 0 && H > 0 && d % H == 0);
+  if (M == 0) return AMPCONV_OK;
+  AMPCONV_REQUIRE(qkv && lse && slot_dst && dst_src && slots && weights);
+  const int hd = d / H;
+  const int tiles = (F + 15) / 16;
+  dim3 grid((unsigned)M, (unsigned)(tiles * tiles));
+  size_t smem = (size_t)2 * 16 * (hd + 1) * sizeof(float);
+  attn_weights_f32_kernel<<<grid, 256, smem, as_stream(stream_)>>>(qkv, lse, slot_dst, dst_src, nullptr, slots, weights, F, d,
+                                                                  H, 1.0f / sqrtf((float)hd));
+  AMPCONV_CHECK_LAUNCH();
   return AMPCONV_OK;
 }
 

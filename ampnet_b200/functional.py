@@ -49,6 +49,46 @@ def _stream(dev):
     return _lib.stream_ptr(torch.cuda.current_stream(dev))
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Status word of the tcgen05 kernels.  Every mbarrier wait in them is bounded; on a time-out the kernel records
+# `code | CTA << 16` in its workspace and drains instead of hanging the GPU -- the output of that launch is then garbage.
+# The product path therefore copies the word to pinned host memory at the end of every forward / backward (asynchronously,
+# no synchronisation) and raises at the next layer call (or at ``check_status(sync=True)``) if any copy came back non-zero.
+# ---------------------------------------------------------------------------------------------------------------------
+_pending_status = []     # (pinned int32[1], event, label)
+
+
+class KernelProtocolError(RuntimeError):
+    pass
+
+
+def _post_status(ws, label):
+    host = torch.zeros(1, dtype=torch.int32).pin_memory()
+    host.copy_(ws[1:2], non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    _pending_status.append((host, ev, label))
+
+
+def check_status(sync=False):
+    """Raises KernelProtocolError if a tcgen05 launch reported a pipeline time-out.  sync=False only looks at status copies
+    that have already arrived (free); sync=True waits for all of them."""
+    keep, bad = [], None
+    for host, ev, label in _pending_status:
+        if sync:
+            ev.synchronize()
+        if not ev.query():
+            keep.append((host, ev, label))
+            continue
+        v = int(host.item())
+        if v != 0 and bad is None:
+            bad = (v, label)
+    _pending_status[:] = keep
+    if bad is not None:
+        raise KernelProtocolError(f"tcgen05 kernel pipeline time-out in {bad[1]}: wait id {bad[0] & 0xffff} in CTA {bad[0] >> 16}; "
+                                  "the results of that call are invalid")
+
+
 def _param_grad_ws(out_dim, in_dim, dev):
     nbytes = ctypes.c_size_t(0)
     _lib.call("ampconv_param_grad_workspace_bytes", _lib.i32(out_dim), _lib.i32(in_dim), ctypes.byref(nbytes))
@@ -124,8 +164,9 @@ def _forward_bf16(x, graph, w_in, b_in, w_out, b_out, num_heads):
               ws, _lib.size_t(ws.numel() * 4), st)
     _lib.call("ampconv_out_proj_tc", agg, w_out, b_out, graph.has_in, out,
               _lib.i64(n), _lib.i32(f), _lib.i32(d), ws, st)
+    _post_status(ws, "AMPConv forward (bf16)")
     saved = _Saved("bf16", graph, (n, e, f, d, num_heads), None, agg, None, bf16=(q, k, v, lse2, ws),
-                   inputs=(x, w_in.detach(), b_in.detach()))
+                   inputs=(x, w_in.detach().clone(), b_in.detach().clone()))
     return out, saved
 
 
@@ -187,6 +228,7 @@ def _backward_bf16(saved, x, w_in, w_out, d_out):
     _lib.call("ampconv_qkv_proj_bwd_input_tc", d_qkv, w_in, d_x, _lib.i64(rows), _lib.i32(d), bws, st)
     _lib.call("ampconv_qkv_proj_bwd_params_tc", x, d_qkv, d_w_in, d_b_in,
               _lib.i64(rows), _lib.i32(d), ws, _lib.size_t(ws.numel()), bws, st)
+    _post_status(bws, "AMPConv backward (bf16)")
     return d_x, d_w_in, d_b_in, d_w_out, d_b_out
 
 
@@ -323,7 +365,7 @@ class _AMPConvFunction(torch.autograd.Function):
         ctx.saved_state = saved
         if holder is not None:
             holder["saved"] = saved
-            holder["params"] = (w_out.detach(), b_out.detach())
+            holder["params"] = (w_out.detach().clone(), b_out.detach().clone())   # snapshot: the lazy side outputs must not see a later optimiser step
         return out
 
     @staticmethod
@@ -354,23 +396,59 @@ def check_inputs(x, edge_index, embed_dim, num_heads):
         raise TypeError("x and edge_index must be on the same device")
 
 
-def amp_conv(x, graph, w_in, b_in, w_out, b_out, num_heads, mode="fp32", holder=None):
+def check_params(x, w_in, b_in, w_out, b_out):
+    """The C ABI takes raw fp32 device pointers: a module after .half() / .double(), or with parameters on another device,
+    must raise here instead of being reinterpreted."""
+    d = w_in.shape[1] if w_in.dim() == 2 else -1
+    want = {"in_proj_weight": (w_in, (3 * d, d)), "in_proj_bias": (b_in, (3 * d,)),
+            "out_proj.weight": (w_out, (d, d)), "out_proj.bias": (b_out, (d,))}
+    for name, (t, shape) in want.items():
+        if t.dtype != torch.float32:
+            raise TypeError(f"{name} must be float32 (got {t.dtype}): the kernels read fp32 parameters")
+        if t.device != x.device:
+            raise TypeError(f"{name} is on {t.device}, x on {x.device}")
+        if tuple(t.shape) != shape:
+            raise ValueError(f"{name} has shape {tuple(t.shape)}, expected {shape}")
+
+
+def amp_conv(x, graph, w_in, b_in, w_out, b_out, num_heads, mode="auto", holder=None):
+    check_params(x, w_in, b_in, w_out, b_out)
+    check_status()
     mode = resolve_mode(mode, x.shape[1] // w_in.shape[1], w_in.shape[1], num_heads)
     return _AMPConvFunction.apply(x.contiguous(), w_in.contiguous(), b_in.contiguous(), w_out.contiguous(),
                                   b_out.contiguous(), graph, num_heads, mode, holder)
 
 
-def attention_weights(saved):
-    """Head-averaged coefficients [E, F, F] in original edge order (``attn_output_weights``)."""
+def attention_weights(saved, edge_ids=None):
+    """Head-averaged coefficients in original edge order (``attn_output_weights``): [E, F, F], or [len(edge_ids), F, F] for
+    the listed edge ids (columns of ``edge_index``) -- the chunked form: at the ogbn-arxiv shape all of [E, F, F] is 76 GB."""
     saved.ensure_fp32_views()
     n, e, f, d, h = saved.shape
     g = saved.graph
     dev = saved.qkv.device
-    w = torch.empty((e, f, f), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        _lib.call("ampconv_attn_weights_f32", saved.qkv, saved.lse, g.dst_rowptr, g.dst_src, g.dst_eid, w,
-                  _lib.i64(n), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(h), _stream(dev))
+        if edge_ids is None:
+            w = torch.empty((e, f, f), dtype=torch.float32, device=dev)
+            _lib.call("ampconv_attn_weights_f32", saved.qkv, saved.lse, g.dst_rowptr, g.dst_src, g.dst_eid, w,
+                      _lib.i64(n), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(h), _stream(dev))
+            return w
+        edge_ids = torch.as_tensor(edge_ids, device=dev).to(torch.int64).reshape(-1)
+        if edge_ids.numel() and (int(edge_ids.min()) < 0 or int(edge_ids.max()) >= e):
+            raise IndexError("edge id out of range")
+        slots = g.slot_of_eid[edge_ids].contiguous()
+        w = torch.empty((edge_ids.numel(), f, f), dtype=torch.float32, device=dev)
+        _lib.call("ampconv_attn_weights_slots_f32", saved.qkv, saved.lse, g.slot_dst, g.dst_src, slots,
+                  _lib.i64(slots.numel()), w, _lib.i32(f), _lib.i32(d), _lib.i32(h), _stream(dev))
     return w
+
+
+def attention_weights_chunks(saved, chunk_edges=4096):
+    """Generator over (edge_ids, weights[len, F, F]) slices covering every edge in original order."""
+    e = saved.shape[1]
+    dev = saved.graph.device
+    for lo in range(0, e, chunk_edges):
+        ids = torch.arange(lo, min(e, lo + chunk_edges), device=dev)
+        yield ids, attention_weights(saved, ids)
 
 
 def edge_output(saved, w_out, b_out):

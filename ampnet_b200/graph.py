@@ -45,6 +45,25 @@ class Graph:
         # longest-processing-time-first node orders for the persistent tcgen05 kernels (dynamic scheduler)
         self.order_dst = torch.argsort(self.dst_rowptr[1:] - self.dst_rowptr[:-1], descending=True).to(torch.int32)
         self.order_src = torch.argsort(self.src_rowptr[1:] - self.src_rowptr[:-1], descending=True).to(torch.int32)
+        self._slot_dst = None
+        self._slot_of_eid = None
+
+    @property
+    def slot_dst(self):
+        """Destination node of every destination-sorted slot [E] (int32)."""
+        if self._slot_dst is None:
+            deg = (self.dst_rowptr[1:] - self.dst_rowptr[:-1]).to(torch.int64)
+            self._slot_dst = torch.repeat_interleave(torch.arange(self.num_nodes, device=self.device, dtype=torch.int32), deg)
+        return self._slot_dst
+
+    @property
+    def slot_of_eid(self):
+        """Destination-sorted slot of every original edge id [E] (int32): the inverse of dst_eid."""
+        if self._slot_of_eid is None:
+            inv = torch.empty(self.num_edges, dtype=torch.int32, device=self.device)
+            inv[self.dst_eid.to(torch.int64)] = torch.arange(self.num_edges, device=self.device, dtype=torch.int32)
+            self._slot_of_eid = inv
+        return self._slot_of_eid
 
 
 _cache = {}
@@ -56,15 +75,18 @@ def _evict(key):
 
 def get_graph(edge_index, num_nodes):
     """Cached on the identity, version and shape of ``edge_index`` (both AMPConv layers of a model
-    and every training step on a fixed graph share one build)."""
+    and every training step on a fixed graph share one build).  The key relies on torch's version counter: a buffer
+    rewritten behind torch's back (``.data`` writes, a c10d receive into it, an external kernel) must be followed by
+    ``clear_cache()`` -- or build a ``Graph`` explicitly and call ``functional.amp_conv`` with it."""
     key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), int(num_nodes),
            str(edge_index.device))
     hit = _cache.get(key)
     if hit is not None and hit[0]() is not None:
+        _cache[key] = _cache.pop(key)          # most recently used last
         return hit[1]
     g = Graph(edge_index, num_nodes)
-    if len(_cache) > 16:
-        _cache.clear()
+    while len(_cache) >= 16:
+        _cache.pop(next(iter(_cache)))         # evict the least recently used entry only
     # the weak reference ties the entry's validity to the storage the key's data_ptr came from
     _cache[key] = (weakref.ref(edge_index, lambda _r, k=key: _evict(k)), g)
     return g

@@ -32,6 +32,8 @@ WORKLOADS = {
     "C2": dict(n=750, e=3000, f=20, d=128, h=4, desc="GraphSAINT-Cora subgraph shape"),
     "C3": dict(n=400, e=8400, f=2, d=3, h=1, desc="XOR graph shape"),
     "C4s": dict(n=16934, e=116624, f=128, d=64, h=4, desc="C4 token shape at 1/10 of the nodes and edges"),
+    "C5": dict(n=2449029, e=61859140, f=100, d=64, h=8, desc="synthetic ogbn-products shape (multi-GPU only)"),
+    "C5s": dict(n=122451, e=3092957, f=100, d=64, h=8, desc="ogbn-products token shape at 1/20 of the nodes and edges"),
 }
 METRIC = "AMPConv fwd+bwd edges/sec"
 
@@ -92,8 +94,8 @@ class ClockSampler:
 
 def make_problem(spec, graph_kind, seed=1234):
     """Synthetic inputs of SURVEY.md section 8(d): x ~ N(0,1), d_out ~ N(0,1), uniform or skewed graph."""
-    from oracle import cases  # input generator only (numpy); no reference/oracle compute involved
-    return cases.make_graph(graph_kind, spec["n"], spec["e"], seed=7 + seed)
+    from ampnet_b200.loader import make_graph
+    return make_graph(graph_kind, spec["n"], spec["e"], seed=7 + seed)
 
 
 def init_conv(conv, seed=0):
@@ -112,27 +114,46 @@ def init_conv(conv, seed=0):
 # CPU arm: the reference's eager op chain (oracle/torch_port.py) on a bounded edge sample
 # ------------------------------------------------------------------------------------------
 def cpu_sample_run(spec, sample_edges, sample_nodes, reps, warmup):
-    from oracle import cases
-    from oracle.torch_port import AMPConvPort, fwd_bwd_chunked
+    """The CPU arm (the one place bench.py executes oracle/): the reference's own AMPConv (oracle/_ref/amp_conv.py, the
+    verbatim copy build() stages, behind the PyG stand-in) when present -- kind "reference" -- else the op-for-op port
+    (oracle/torch_port.py, kind "port").  The edge sample is processed in chunks (each chunk is one forward + backward of
+    the layer over the chunk's edges: every op on the path is per-edge or a linear scatter, so time is linear in edges)."""
+    from ampnet_b200.loader import make_graph
+    from oracle import reference_loader
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     f, d, h = spec["f"], spec["d"], spec["h"]
     g = torch.Generator().manual_seed(1234)
     x = torch.randn(sample_nodes, f * d, generator=g)
     d_out = torch.randn(sample_nodes, f * d, generator=g)
-    ei = torch.from_numpy(cases.make_graph("uniform", sample_nodes, sample_edges, seed=7))
-    conv = AMPConvPort(d, h)
-    init_conv(conv)
+    ei = torch.from_numpy(make_graph("uniform", sample_nodes, sample_edges, seed=7))
     chunk = max(64, min(sample_edges, int(2.5e8 // max(1, h * f * f))))   # keeps [chunk,H,F,F] fp32 near 1 GB
+    if reference_loader.amp_conv_path() is not None:
+        kind = "reference"
+        conv = reference_loader.load_amp_conv_module().AMPConv(embed_dim=d, num_heads=h)
+
+        def run():
+            xin = x.detach().requires_grad_(True)
+            for lo in range(0, sample_edges, chunk):
+                out = conv(xin, ei[:, lo:lo + chunk])
+                out.backward(d_out)
+    else:
+        kind = "port"
+        from oracle.torch_port import AMPConvPort, fwd_bwd_chunked
+        conv = AMPConvPort(d, h)
+
+        def run():
+            fwd_bwd_chunked(conv, x, ei, d_out, chunk)
+    init_conv(conv)
     times = []
     for it in range(warmup + reps):
         conv.zero_grad()
         t0 = time.perf_counter()
-        fwd_bwd_chunked(conv, x, ei, d_out, chunk)
+        run()
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
-    return dict(times=times, cores=cores, chunk=chunk)
+    return dict(times=times, cores=cores, chunk=chunk, kind=kind)
 
 
 def run_reference(args):
@@ -153,8 +174,10 @@ def run_reference(args):
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {spec['desc']} (N={spec['n']}, E={spec['e']}, F={spec['f']}, "
                                f"d={spec['d']}, H={spec['h']}), one AMPConv layer fwd+bwd, {args.graph} graph seed 7",
-                   "mode": "fp32 (the reference's eager op chain on the host cores)", "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "edges/s", "cores": r["cores"], "kind": "port", "sample": sample},
+                   "mode": "fp32 (the reference's AMPConv on the host cores: " +
+                           ("oracle/_ref/amp_conv.py, verbatim, behind the PyG stand-in)" if r["kind"] == "reference"
+                            else "op-for-op port oracle/torch_port.py)"), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "edges/s", "cores": r["cores"], "kind": r["kind"], "sample": sample},
         "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -314,10 +337,14 @@ def run_ours(args):
     feed.release()
 
     # ---- per-kernel durations of the attention kernels (CUDA events on the launching stream)
-    kern_ms = profile_attention_kernels(conv, x_dev, edge_index, d_out, args.mode, reps=max(2, min(args.steps, 5)))
+    if F_.resolve_mode(args.mode, f, d, h) == "bf16g":
+        # head-group decomposition (two launches per pass): per-kernel roofline not itemised
+        kern_ms = {"attn_fwd": float("nan"), "attn_bwd_dq": float("nan"), "attn_bwd_dkv": ms_step}
+    else:
+        kern_ms = profile_attention_kernels(conv, x_dev, edge_index, d_out, args.mode, reps=max(2, min(args.steps, 5)))
     alg = algorithmic_bytes(spec, args.mode)
     pk = peaks()
-    dominant = max(kern_ms, key=kern_ms.get)
+    dominant = max(kern_ms, key=lambda k_: kern_ms[k_] if kern_ms[k_] == kern_ms[k_] else -1.0)
     achieved = alg[dominant] / (kern_ms[dominant] * 1e-3) / 1e9
     traffic, traffic_src = ncu_traffic(args.workload, dominant)
     # the unit that actually binds these kernels is MUFU (exp2): H*F^2 exponentials per edge and pass at 16 / clk / SM
@@ -338,9 +365,10 @@ def run_ours(args):
         se = min(spec["e"], args.cpu_sample_edges)
         sn = min(spec["n"], max(2, se // 2))
         r = cpu_sample_run(spec, se, sn, reps=2, warmup=1)
-        cpu = {"value": se / float(np.mean(r["times"])), "unit": "edges/s", "cores": r["cores"], "kind": "port",
+        cpu = {"value": se / float(np.mean(r["times"])), "unit": "edges/s", "cores": r["cores"], "kind": r["kind"],
                "sample": f"{se} edges over a {sn}-node slice at the {args.workload} token shape, fp32, "
-                         f"reference op chain (oracle/torch_port.py), edge-chunked by {r['chunk']}"}
+                         + ("the reference's own amp_conv.py (oracle/_ref, verbatim)" if r["kind"] == "reference"
+                            else "reference op chain (oracle/torch_port.py)") + f", edge-chunked by {r['chunk']}"}
     line = {
         "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",

@@ -115,6 +115,14 @@ AMPCONV_API int ampconv_attn_weights_f32(const float* qkv, const float* lse, con
                              const int32_t* dst_src, const int32_t* dst_eid, float* weights,
                              int64_t num_nodes, int64_t num_edges, int F, int d, int H, void* stream);
 
+/* Chunked form (at the ogbn-arxiv shape all of [E,F,F] is 76 GB): weights[m,:,:] for the M listed
+ * destination-sorted slots; slot_dst[p] = destination node of slot p, for every slot ([E]).  The callers
+ * (synthetic_benchmark/visualize_attention_coefficients.py:221-232) index the result by original edge id; the host
+ * maps ids to slots and walks them in slices. */
+AMPCONV_API int ampconv_attn_weights_slots_f32(const float* qkv, const float* lse, const int32_t* slot_dst,
+                                   const int32_t* dst_src, const int32_t* slots, int64_t M, float* weights,
+                                   int F, int d, int H, void* stream);
+
 /* Per-edge attention output after out_proj in ORIGINAL edge order (the attn_output side output,
  * amp_conv.py:39): edge_out[dst_eid[p], i, :] = (softmax(q k^T) v)[i,:] @ Wo^T + bo. */
 AMPCONV_API int ampconv_edge_output_f32(const float* qkv, const float* lse, const int32_t* dst_rowptr,
@@ -175,8 +183,9 @@ AMPCONV_API int ampconv_qkv_proj_bf16(const float* x, const float* in_proj_weigh
 /* Fused attention + mean aggregation on tensor cores (same contract as ampconv_attn_fwd_f32).
  * q/k/v: bf16 [N,F,d] from ampconv_qkv_proj_bf16; agg: fp32 [N,F,d];
  * lse2[p,h,i] = log2-sum-exp2 of the (log2-domain) scores of edge slot p, shape [E, H, roundup4(F)];
- * order: optional node processing order [N] (NULL = 0..N-1); workspace >= 256 bytes (scheduler counter
- * and a status word, see ampconv_bf16_status). */
+ * order: optional node processing order [N] (NULL = 0..N-1); workspace >= 256 bytes, ZEROED BY THE CALLER once per
+ * layer call: int[0], [2], [4] are scheduler counters (reset by each launch), int[1] is the family's status word --
+ * the first pipeline time-out of any launch that shares the workspace sticks there (see ampconv_bf16_status). */
 AMPCONV_API int ampconv_attn_fwd_bf16(const void* q, const void* k, const void* v,
                           const int32_t* dst_rowptr, const int32_t* dst_src, const float* inv_deg,
                           const int32_t* order, float* agg, float* lse2,

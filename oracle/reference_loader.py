@@ -11,17 +11,40 @@ from . import pyg_stub
 
 REFERENCE_ROOT = os.environ.get("AMPNET_REFERENCE_ROOT", "/root/reference")
 _AMP_CONV = os.path.join(REFERENCE_ROOT, "src", "ampnet", "conv", "amp_conv.py")
+# oracle/_ref/: a byte-for-byte copy of the reference's amp_conv.py made by __graft_entry__.build() in the build container
+# (git-ignored, so it never enters the history; it travels to the GPU box with the snapshot like the built .so).  It lets
+# bench.py time the REFERENCE ITSELF on the GPU box's host cores (cpu_baseline.kind = "reference").
+_REF_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+_AMP_CONV_COPY = os.path.join(_REF_DIR, "amp_conv.py")
 
 
 def available():
     return os.path.isfile(_AMP_CONV)
 
 
-def load_amp_conv_module():
+def stage_reference_copy():
+    """build(): copy the reference's hot-path file into oracle/_ref/ (no-op where /root/reference is absent)."""
     if not available():
+        return os.path.isfile(_AMP_CONV_COPY)
+    import shutil
+    os.makedirs(_REF_DIR, exist_ok=True)
+    shutil.copyfile(_AMP_CONV, _AMP_CONV_COPY)
+    return True
+
+
+def amp_conv_path():
+    """The reference's amp_conv.py where it lies (build container), else the staged copy (GPU box), else None."""
+    if available():
+        return _AMP_CONV
+    return _AMP_CONV_COPY if os.path.isfile(_AMP_CONV_COPY) else None
+
+
+def load_amp_conv_module():
+    path = amp_conv_path()
+    if path is None:
         raise FileNotFoundError(_AMP_CONV)
     pyg_stub.install()
-    spec = importlib.util.spec_from_file_location("_reference_amp_conv", _AMP_CONV)
+    spec = importlib.util.spec_from_file_location("_reference_amp_conv", path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod

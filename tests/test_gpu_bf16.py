@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import load_golden, rel_err
+from conftest import assert_close, load_golden, rel_err
 from test_gpu_parity import GRAD_KEYS, _make_conv, _run
 
 pytestmark = pytest.mark.gpu
@@ -23,10 +23,10 @@ def test_bf16_mode_matches_reference_golden(name):
     conv = _make_conv(g["d"], g["h"], g["params"], dev, mode="bf16")
     res = _run(conv, g["x"], g["edge_index"], g["d_out"], dev)
     assert _status(conv) == 0
-    assert rel_err(res["out"], g["out"]) < TOL_BF16
-    assert rel_err(res["d_x"], g["d_x"]) < TOL_BF16
+    assert_close(res["out"], g["out"], TOL_BF16)
+    assert_close(res["d_x"], g["d_x"], TOL_BF16)
     for k in GRAD_KEYS:
-        assert rel_err(res[k], g[k]) < TOL_BF16, k
+        assert_close(res[k], g[k], TOL_BF16, k)
     deg = np.bincount(g["edge_index"][1], minlength=g["n"])
     assert np.all(res["out"][deg == 0] == 0.0)
     we = g["weight_edges"]
@@ -50,10 +50,10 @@ def test_bf16_mode_matches_numpy_oracle(shape):
     assert _status(conv) == 0
     ref = numpy_oracle.backward(x, ei, p["in_proj_weight"], p["in_proj_bias"], p["out_proj_weight"],
                                 p["out_proj_bias"], shape["h"], d_out)
-    assert rel_err(res["out"], ref["out"]) < TOL_BF16
-    assert rel_err(res["d_x"], ref["d_x"]) < TOL_BF16
+    assert_close(res["out"], ref["out"], TOL_BF16)
+    assert_close(res["d_x"], ref["d_x"], TOL_BF16)
     for k in GRAD_KEYS:
-        assert rel_err(res[k], ref[k]) < TOL_BF16, k
+        assert_close(res[k], ref[k], TOL_BF16, k)
 
 
 def test_bf16_mode_rejects_unsupported_shapes_and_auto_falls_back_to_fp32_kernels():

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import golden_names, load_golden, rel_err
+from conftest import assert_close, golden_names, load_golden, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -47,10 +47,10 @@ def test_strict_mode_matches_reference_goldens(name):
     g = load_golden(name)
     conv = _make_conv(g["d"], g["h"], g["params"], dev)
     res = _run(conv, g["x"], g["edge_index"], g["d_out"], dev)
-    assert rel_err(res["out"], g["out"]) < TOL_STRICT
-    assert rel_err(res["d_x"], g["d_x"]) < TOL_STRICT
+    assert_close(res["out"], g["out"], TOL_STRICT)
+    assert_close(res["d_x"], g["d_x"], TOL_STRICT)
     for k in GRAD_KEYS:
-        assert rel_err(res[k], g[k]) < TOL_STRICT, k
+        assert_close(res[k], g[k], TOL_STRICT, k)
     # exact zeros for nodes nobody sends to
     deg = np.bincount(g["edge_index"][1], minlength=g["n"])
     assert np.all(res["out"][deg == 0] == 0.0)
@@ -62,7 +62,7 @@ def test_strict_mode_matches_reference_goldens(name):
     assert np.allclose(w.sum(-1).cpu().numpy(), 1.0, atol=1e-4)
     ao = conv.attn_output
     assert tuple(ao.shape) == (g["e"], g["f"], g["d"])
-    assert rel_err(ao.cpu().numpy()[we], g["attn_output"]) < TOL_STRICT
+    assert_close(ao.cpu().numpy()[we], g["attn_output"], TOL_STRICT)
 
 
 def test_graph_build_matches_numpy():
@@ -121,10 +121,10 @@ def test_strict_mode_matches_numpy_oracle_on_seeded_inputs(shape):
     res = _run(conv, x, ei, d_out, dev)
     ref = numpy_oracle.backward(x, ei, p["in_proj_weight"], p["in_proj_bias"], p["out_proj_weight"],
                                 p["out_proj_bias"], shape["h"], d_out)
-    assert rel_err(res["out"], ref["out"]) < TOL_STRICT
-    assert rel_err(res["d_x"], ref["d_x"]) < TOL_STRICT
+    assert_close(res["out"], ref["out"], TOL_STRICT)
+    assert_close(res["d_x"], ref["d_x"], TOL_STRICT)
     for k in GRAD_KEYS:
-        assert rel_err(res[k], ref[k]) < TOL_STRICT, k
+        assert_close(res[k], ref[k], TOL_STRICT, k)
 
 
 def test_edge_permutation_invariance_and_linearity_in_upstream_gradient():
@@ -141,9 +141,9 @@ def test_edge_permutation_invariance_and_linearity_in_upstream_gradient():
     conv.zero_grad()
     b = _run(conv, x, ei[:, perm], d_out, dev)
     w_b = conv.attn_output_weights.cpu().numpy()
-    assert rel_err(b["out"], a["out"]) < 1e-5
-    assert rel_err(b["d_x"], a["d_x"]) < 1e-5
+    assert_close(b["out"], a["out"], 1e-5)
+    assert_close(b["d_x"], a["d_x"], 1e-5)
     assert np.abs(w_b - w_a[perm]).max() < 1e-6
     conv.zero_grad()
     c = _run(conv, x, ei, 2.0 * d_out, dev)
-    assert rel_err(c["d_x"], 2.0 * a["d_x"]) < 1e-5
+    assert_close(c["d_x"], 2.0 * a["d_x"], 1e-5)
