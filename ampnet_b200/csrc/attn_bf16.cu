@@ -84,7 +84,8 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
                      const __grid_constant__ CUtensorMap mapV, const int32_t* __restrict__ rowptr,
                      const int32_t* __restrict__ dst_src, const float* __restrict__ inv_deg,
                      const int32_t* __restrict__ order, int* __restrict__ counter, int* __restrict__ status,
-                     float* __restrict__ agg, float* __restrict__ lse2, int N, int F, long long* __restrict__ prof) {
+                     float* __restrict__ agg, float* __restrict__ lse2, int N, int F, int accumulate,
+                     long long* __restrict__ prof) {
   constexpr int H = kD / HD;        // heads
   constexpr int HL = H / 2;         // heads per softmax warpgroup (head h belongs to warpgroup h & 1)
   static_assert(H % 2 == 0, "this kernel splits heads between two warpgroups");
@@ -141,6 +142,7 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       pb = __shfl_sync(0xffffffffu, pb, 0);
       pe = __shfl_sync(0xffffffffu, pe, 0);
       if (node >= 0 && pe == pb) {
+        if (accumulate) continue;   // a later ring phase: the node's rows already hold the earlier phases' sum
         float4* z = reinterpret_cast<float4*>(agg + (int64_t)node * F * kD);
         for (int i = lane; i < F * (kD / 4); i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         continue;
@@ -368,9 +370,15 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
           for (int hl = 0; hl < HL; ++hl) {
             float4* o4 = reinterpret_cast<float4*>(dst + (2 * hl + b) * HD);
 #pragma unroll
-            for (int x = 0; x < HD; x += 4)
-              o4[x >> 2] = make_float4(__uint_as_float(o[hl][x]) * ns.inv_deg, __uint_as_float(o[hl][x + 1]) * ns.inv_deg,
-                                       __uint_as_float(o[hl][x + 2]) * ns.inv_deg, __uint_as_float(o[hl][x + 3]) * ns.inv_deg);
+            for (int x = 0; x < HD; x += 4) {
+              float4 r = make_float4(__uint_as_float(o[hl][x]) * ns.inv_deg, __uint_as_float(o[hl][x + 1]) * ns.inv_deg,
+                                     __uint_as_float(o[hl][x + 2]) * ns.inv_deg, __uint_as_float(o[hl][x + 3]) * ns.inv_deg);
+              if (accumulate) {   // ring phases (multi-GPU): the mean is a sum over all phases' edges, inv_deg is the full one
+                const float4 a = o4[x >> 2];
+                r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w;
+              }
+              o4[x >> 2] = r;
+            }
           }
         }
       }
@@ -404,10 +412,13 @@ static int attn_fwd_bf16_impl(const void* q, const void* k, const void* v,
                               const int32_t* dst_rowptr, const int32_t* dst_src, const float* inv_deg,
                               const int32_t* order, float* agg, float* lse2,
                               int64_t N, int64_t N_kv, int64_t E, int F, int d, int H,
-                              void* workspace, size_t workspace_bytes, void* stream_, long long* prof) {
+                              void* workspace, size_t workspace_bytes, void* stream_, long long* prof,
+                              int64_t n_work = -1, int accumulate = 0) {
   AMPCONV_REQUIRE(N >= 0 && E >= 0 && F > 0 && d > 0 && H > 0 && d % H == 0);
   if (!ampconv_attn_bf16_supported(F, d, H)) return AMPCONV_ERR_UNSUPPORTED;
-  if (N == 0) return AMPCONV_OK;
+  if (n_work < 0) n_work = N;        // length of the `order` work list (all destinations unless a ring phase lists fewer)
+  AMPCONV_REQUIRE(n_work <= N && (n_work == N || order != nullptr));
+  if (N == 0 || n_work == 0) return AMPCONV_OK;
   AMPCONV_REQUIRE(q && k && v && dst_rowptr && inv_deg && agg && workspace && (E == 0 || (dst_src && lse2)));
   if (workspace_bytes < 256) return AMPCONV_ERR_WORKSPACE;
   cudaStream_t stream = as_stream(stream_);
@@ -419,14 +430,14 @@ static int attn_fwd_bf16_impl(const void* q, const void* k, const void* v,
   int* status = counter + 1;
   AMPCONV_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(int), stream));   // the status word (counter + 1) is the caller's: zeroed once per layer call
   const size_t smem = sizeof(FwdSmem) + 1024;
-  const int grid = (int)(N < sm_count() ? N : sm_count());
+  const int grid = (int)(n_work < sm_count() ? n_work : sm_count());
   const int hd = d / H;
 #define AMP_LAUNCH_FWD(HDV, PROFV)                                                                                    \
   do {                                                                                                                \
     AMPCONV_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_bf16_kernel<HDV, PROFV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                           (int)smem));                                                                \
     attn_fwd_bf16_kernel<HDV, PROFV><<<grid, kFwdThreads, smem, stream>>>(mq, mk, mv, dst_rowptr, dst_src, inv_deg, order, \
-                                                                         counter, status, agg, lse2, (int)N, F, prof);  \
+                                                                         counter, status, agg, lse2, (int)n_work, F, accumulate, prof);  \
   } while (0)
   if (hd == 16) {
     if (prof) AMP_LAUNCH_FWD(16, true); else AMP_LAUNCH_FWD(16, false);
@@ -469,6 +480,22 @@ extern "C" int ampconv_attn_fwd_bf16_part(const void* q, const void* k, const vo
   AMPCONV_REQUIRE(num_kv_nodes > 0 || E == 0);
   return attn_fwd_bf16_impl(q, k, v, dst_rowptr, dst_src, inv_deg, order, agg, lse2, num_nodes,
                             num_kv_nodes > 0 ? num_kv_nodes : 1, E, F, d, H, workspace, workspace_bytes, stream_, nullptr);
+}
+
+// Ring-phase variant (multi-GPU, ampnet_b200/distributed.py): the rank's edges are split by the owner of their source; one
+// launch per phase over the `n_work` destinations listed in `order` that have an edge in the phase.  accumulate = 0: first
+// phase (rows of destinations without an edge are zero-filled, results overwrite agg); accumulate = 1: agg += this phase.
+// rowptr / dst_src / lse2 are the phase's own (lse2 indexed by the phase's destination-sorted slots).
+extern "C" int ampconv_attn_fwd_bf16_phase(const void* q, const void* k, const void* v,
+                                           const int32_t* dst_rowptr, const int32_t* dst_src, const float* inv_deg,
+                                           const int32_t* order, int64_t n_work, int accumulate, float* agg, float* lse2,
+                                           int64_t num_nodes, int64_t num_kv_nodes, int64_t E,
+                                           int F, int d, int H, void* workspace, size_t workspace_bytes, void* stream_) {
+  AMPCONV_REQUIRE(num_kv_nodes > 0 || E == 0);
+  AMPCONV_REQUIRE(n_work >= 0 && order != nullptr);
+  return attn_fwd_bf16_impl(q, k, v, dst_rowptr, dst_src, inv_deg, order, agg, lse2, num_nodes,
+                            num_kv_nodes > 0 ? num_kv_nodes : 1, E, F, d, H, workspace, workspace_bytes, stream_, nullptr,
+                            n_work, accumulate);
 }
 
 // Reads back the protocol status word written by the bf16 kernels (0 = ok).  Synchronises the stream.

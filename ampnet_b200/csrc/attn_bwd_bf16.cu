@@ -138,7 +138,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
                      const int32_t* __restrict__ slot_of, const int32_t* __restrict__ order,
                      const float* __restrict__ lse2, float* __restrict__ delta, float* __restrict__ d_qkv, int* __restrict__ counter, int* __restrict__ status,
                      int N, int F, float out_scale0, float out_scale1, int out_ld, int out_c0, int out_c1,
-                     uint16_t* __restrict__ halo_bf16, int halo_from, long long* __restrict__ prof) {
+                     uint16_t* __restrict__ halo_bf16, int halo_from, int accumulate, long long* __restrict__ prof) {
   using Smem = BwdSmem<MODE>;
   constexpr int NS = Smem::NS;
   constexpr int H = kD / HD;
@@ -224,6 +224,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       if (node >= 0 && ee == eb) {
         // node without edges in this pass: its gradient rows are zero (halo sources always have an edge)
         if (halo_bf16 != nullptr && node >= halo_from) continue;
+        if (accumulate) continue;   // a later ring phase: the node's rows already hold the earlier phases' sum
         const int nblk = MODE == MODE_DQ ? 1 : 2;
         for (int i = lane; i < F * nblk * (kD / 4); i += 32) {
           const int r = i / (nblk * (kD / 4)), rem = i - r * (nblk * (kD / 4));
@@ -465,8 +466,14 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
           }
           if (row_ok) {
 #pragma unroll
-            for (int x = 0; x < 16; x += 4)
-              *reinterpret_cast<float4*>(o + 16 * c4 + x) = make_float4(v[x], v[x + 1], v[x + 2], v[x + 3]);
+            for (int x = 0; x < 16; x += 4) {
+              float4 r = make_float4(v[x], v[x + 1], v[x + 2], v[x + 3]);
+              if (accumulate) {   // ring phases (multi-GPU): dQ is a sum over all phases' edges
+                const float4 pr = *reinterpret_cast<const float4*>(o + 16 * c4 + x);
+                r.x += pr.x; r.y += pr.y; r.z += pr.z; r.w += pr.w;
+              }
+              *reinterpret_cast<float4*>(o + 16 * c4 + x) = r;
+            }
           }
         }
         tc_fence_before();
@@ -709,7 +716,7 @@ template <int HD, int MODE>
 int launch_bwd(const CUtensorMap& own0, const CUtensorMap& own1, const CUtensorMap& oth0, const CUtensorMap& oth1,
                const int32_t* rowptr, const int32_t* nbr, const int32_t* slot_of, const int32_t* order, const float* lse2,
                float* delta, float* d_qkv, int* counter, int* status, int N, int F, float s0, float s1, int out_ld, int out_c0,
-               int out_c1, uint16_t* halo_bf16, int halo_from, cudaStream_t stream) {
+               int out_c1, uint16_t* halo_bf16, int halo_from, int accumulate, cudaStream_t stream) {
   const size_t smem = sizeof(BwdSmem<MODE>) + 1024;
   const int grid = N < sm_count() ? N : sm_count();
   long long* prof = g_bwd_prof;
@@ -719,7 +726,7 @@ int launch_bwd(const CUtensorMap& own0, const CUtensorMap& own1, const CUtensorM
                                           (int)smem));                                                                           \
     attn_bwd_bf16_kernel<HD, MODE, NH_, PROF_><<<grid, threads_of(MODE), smem, stream>>>(                                         \
         own0, own1, oth0, oth1, rowptr, nbr, slot_of, order, lse2, delta, d_qkv, counter, status, N, F, s0, s1, out_ld, out_c0,   \
-        out_c1, halo_bf16, halo_from, prof_);                                                                                    \
+        out_c1, halo_bf16, halo_from, accumulate, prof_);                                                                                  \
   } while (0)
   if (prof) {
     if (F > 64) AMP_LAUNCH_BWD(2, true, prof);
@@ -740,17 +747,20 @@ using namespace ampconv;
 
 extern "C" int ampconv_attn_bf16_supported(int F, int d, int H);
 
-// N_own: nodes the pass iterates over (destinations for MODE_DQ, sources for MODE_DKV); N_oth: nodes of the edge tiles.
+// N_own: nodes the pass's tensor maps cover (destinations for MODE_DQ, sources for MODE_DKV); N_oth: nodes of the edge tiles.
+// n_work: length of the `order` work list (-1: all N_own nodes); accumulate: MODE_DQ only, see the *_phase entry points.
 static int bwd_common(int mode, const void* q, const void* k, const void* v, const void* d_agg_bf16,
                       const int32_t* rowptr, const int32_t* nbr, const int32_t* slot_of, const int32_t* order,
                       const float* lse2, float* delta, float* out, int out_ld, int out_c0, int out_c1, int64_t N_dst, int64_t N_kv, int64_t E, int F, int d,
                       int H, void* workspace, size_t workspace_bytes, void* stream_, void* halo_bf16 = nullptr,
-                      int64_t halo_from = 0) {
+                      int64_t halo_from = 0, int64_t n_work = -1, int accumulate = 0) {
   AMPCONV_REQUIRE(N_dst >= 0 && N_kv >= 0 && E >= 0 && F > 0 && d > 0 && H > 0 && d % H == 0);
   if (!ampconv_attn_bf16_supported(F, d, H)) return AMPCONV_ERR_UNSUPPORTED;
   const int64_t N_own = mode == MODE_DQ ? N_dst : N_kv;
-  if (N_own == 0) return AMPCONV_OK;
-  AMPCONV_REQUIRE(q && k && v && d_agg_bf16 && rowptr && out && workspace);
+  if (n_work < 0) n_work = N_own;
+  AMPCONV_REQUIRE(n_work <= N_own && (n_work == N_own || order != nullptr));
+  if (N_own == 0 || n_work == 0) return AMPCONV_OK;
+  AMPCONV_REQUIRE(q && k && v && d_agg_bf16 && rowptr && workspace && (out || halo_bf16));
   AMPCONV_REQUIRE(E == 0 || (nbr && lse2 && delta));
   if (workspace_bytes < 256) return AMPCONV_ERR_WORKSPACE;
   cudaStream_t stream = as_stream(stream_);
@@ -768,17 +778,17 @@ static int bwd_common(int mode, const void* q, const void* k, const void* v, con
   if (mode == MODE_DQ) {
     // dQ = hd^-1/2 * (dS K)
     if (hd == 16)
-      return launch_bwd<16, MODE_DQ>(mq, mg, mk, mv, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)N_own, F,
-                                    inv_sqrt_hd, 0.f, out_ld, out_c0, out_c1, nullptr, 0, stream);
-    return launch_bwd<32, MODE_DQ>(mq, mg, mk, mv, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)N_own, F,
-                                  inv_sqrt_hd, 0.f, out_ld, out_c0, out_c1, nullptr, 0, stream);
+      return launch_bwd<16, MODE_DQ>(mq, mg, mk, mv, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)n_work, F,
+                                    inv_sqrt_hd, 0.f, out_ld, out_c0, out_c1, nullptr, 0, accumulate, stream);
+    return launch_bwd<32, MODE_DQ>(mq, mg, mk, mv, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)n_work, F,
+                                  inv_sqrt_hd, 0.f, out_ld, out_c0, out_c1, nullptr, 0, accumulate, stream);
   }
   // dK = hd^-1/2 * dS^T Q = ln2 * dS^T Q'  (Q' = Q * log2e / sqrt(hd)),  dV = P^T dO
   if (hd == 16)
-    return launch_bwd<16, MODE_DKV>(mk, mv, mq, mg, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)N_own, F,
-                                   ln2, 1.f, out_ld, out_c0, out_c1, reinterpret_cast<uint16_t*>(halo_bf16), (int)halo_from, stream);
-  return launch_bwd<32, MODE_DKV>(mk, mv, mq, mg, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)N_own, F, ln2,
-                                 1.f, out_ld, out_c0, out_c1, reinterpret_cast<uint16_t*>(halo_bf16), (int)halo_from, stream);
+    return launch_bwd<16, MODE_DKV>(mk, mv, mq, mg, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)n_work, F,
+                                   ln2, 1.f, out_ld, out_c0, out_c1, reinterpret_cast<uint16_t*>(halo_bf16), (int)halo_from, 0, stream);
+  return launch_bwd<32, MODE_DKV>(mk, mv, mq, mg, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)n_work, F, ln2,
+                                 1.f, out_ld, out_c0, out_c1, reinterpret_cast<uint16_t*>(halo_bf16), (int)halo_from, 0, stream);
 }
 
 extern "C" int ampconv_attn_bwd_dq_bf16(const void* q, const void* k, const void* v, const void* d_agg_bf16,
@@ -831,6 +841,36 @@ extern "C" int ampconv_attn_bwd_dkv_bf16_halo(const void* q, const void* k, cons
   AMPCONV_REQUIRE(num_own >= 0 && num_own <= num_kv_nodes && (num_own == num_kv_nodes || d_kv_halo != nullptr));
   return bwd_common(MODE_DKV, q, k, v, d_agg_bf16, src_rowptr, src_dst, src_pos, order, lse2, const_cast<float*>(delta), d_kv_own,
                     2 * kD, 0, kD, num_nodes, num_kv_nodes, E, F, d, H, workspace, workspace_bytes, stream, d_kv_halo, num_own);
+}
+
+// Ring-phase variants (multi-GPU, ampnet_b200/distributed.py): one launch per source-owner phase.
+//   _dq_phase : the `n_work` destinations listed in `order` (those with an edge in the phase); accumulate = 0 overwrites d_q
+//               (and zero-fills destinations without an edge), accumulate = 1 adds this phase's contribution; delta is
+//               indexed by the PHASE's destination-sorted slots and consumed by the same phase's _dkv launch.
+//   _dkv_phase: the `n_work` sources listed in `order`, all inside the phase's compact-id range.  Own sources
+//               (halo_from >= num_kv_nodes, d_kv_halo NULL) go to d_kv_own fp32 [num_own*F, 128]; the halo sources of the
+//               phase's owner, compact ids [halo_from, ...), go as bf16 rows to d_kv_halo[(id - halo_from)*F, 128]: the
+//               block that travels to that owner.
+extern "C" int ampconv_attn_bwd_dq_bf16_phase(const void* q, const void* k, const void* v, const void* d_agg_bf16,
+                                              const float* lse2, const int32_t* dst_rowptr, const int32_t* dst_src,
+                                              const int32_t* order, int64_t n_work, int accumulate, float* d_q, float* delta,
+                                              int64_t num_nodes, int64_t num_kv_nodes, int64_t E, int F, int d, int H,
+                                              void* workspace, size_t workspace_bytes, void* stream) {
+  AMPCONV_REQUIRE(n_work >= 0 && order != nullptr);
+  return bwd_common(MODE_DQ, q, k, v, d_agg_bf16, dst_rowptr, dst_src, nullptr, order, lse2, delta, d_q, kD, 0, 0, num_nodes,
+                    num_kv_nodes, E, F, d, H, workspace, workspace_bytes, stream, nullptr, 0, n_work, accumulate);
+}
+
+extern "C" int ampconv_attn_bwd_dkv_bf16_phase(const void* q, const void* k, const void* v, const void* d_agg_bf16,
+                                               const float* lse2, const float* delta, const int32_t* src_rowptr,
+                                               const int32_t* src_dst, const int32_t* src_pos, const int32_t* order,
+                                               int64_t n_work, float* d_kv_own, void* d_kv_halo, int64_t halo_from,
+                                               int64_t num_nodes, int64_t num_kv_nodes, int64_t E, int F, int d, int H,
+                                               void* workspace, size_t workspace_bytes, void* stream) {
+  AMPCONV_REQUIRE(n_work >= 0 && order != nullptr && halo_from >= 0 && (d_kv_own != nullptr || d_kv_halo != nullptr));
+  return bwd_common(MODE_DKV, q, k, v, d_agg_bf16, src_rowptr, src_dst, src_pos, order, lse2, const_cast<float*>(delta), d_kv_own,
+                    2 * kD, 0, kD, num_nodes, num_kv_nodes, E, F, d, H, workspace, workspace_bytes, stream, d_kv_halo,
+                    d_kv_halo ? halo_from : num_kv_nodes, n_work, 0);
 }
 
 // Debug: when set to a device buffer of 64 int64, the next backward launches run the instrumented kernel and fill it

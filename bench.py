@@ -185,6 +185,72 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------
+# Parity check printed with every GPU line: the layer that is about to be timed (same code path, same world size) on small
+# seeded graphs against the CPU oracle (oracle/numpy_oracle.py, the checker -- never the thing measured).  At N > 1 every
+# rank checks its own rows of out / dX and the all-reduced parameter gradients; the JSON line carries the worst error over
+# ranks and the run exits non-zero when a case misses the bf16 bar of BASELINE.json (2e-2).
+# ------------------------------------------------------------------------------------------
+PARITY_CASES = [
+    dict(name="c4_tokens_skewed", n=600, e=4200, f=128, d=64, h=4, graph="skewed"),
+    dict(name="c5_tokens_skewed", n=480, e=3000, f=100, d=64, h=8, graph="skewed"),
+]
+PARITY_TOL = 2e-2
+
+
+def parity_check(dev, world, rank, mode="bf16"):
+    from ampnet_b200 import AMPConv
+    from ampnet_b200.loader import make_inputs
+    from oracle import numpy_oracle
+    cases, worst = [], 0.0
+    for c in PARITY_CASES:
+        n, e, f, d, h = c["n"], c["e"], c["f"], c["d"], c["h"]
+        x, ei, p, d_out = make_inputs(n, e, f, d, h, graph=c["graph"], seed=2024)
+        ref = numpy_oracle.backward(x, ei, p["in_proj_weight"], p["in_proj_bias"], p["out_proj_weight"], p["out_proj_bias"], h, d_out)
+        conv = AMPConv(d, h, mode=mode).to(dev)
+        mha = conv.multi_head_attention
+        with torch.no_grad():
+            mha.in_proj_weight.copy_(torch.from_numpy(p["in_proj_weight"]))
+            mha.in_proj_bias.copy_(torch.from_numpy(p["in_proj_bias"]))
+            mha.out_proj.weight.copy_(torch.from_numpy(p["out_proj_weight"]))
+            mha.out_proj.bias.copy_(torch.from_numpy(p["out_proj_bias"]))
+        eit = torch.from_numpy(ei).to(dev)
+        if world > 1:
+            from ampnet_b200 import distributed as D
+            pg = D.PartitionedGraph(eit, n, world, rank)
+            lo, hi = pg.lo, pg.hi
+            xl = torch.from_numpy(x[lo:hi]).to(dev).requires_grad_(True)
+            out = D.dist_amp_conv(xl, pg, mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight, mha.out_proj.bias, h,
+                                  key=("parity", c["name"]))
+        else:
+            lo, hi = 0, n
+            xl = torch.from_numpy(x).to(dev).requires_grad_(True)
+            out = conv(xl, eit)
+        out.backward(torch.from_numpy(d_out[lo:hi]).to(dev))
+        torch.cuda.synchronize()
+
+        def rel(a, b, scale):
+            return float(np.abs(a.astype(np.float64) - b).max() / max(float(np.abs(scale).max()), 1e-30))
+
+        errs = {"out": rel(out.detach().cpu().numpy(), ref["out"][lo:hi], ref["out"]),
+                "d_x": rel(xl.grad.cpu().numpy(), ref["d_x"][lo:hi], ref["d_x"])}
+        for key, q in (("d_in_proj_weight", mha.in_proj_weight), ("d_in_proj_bias", mha.in_proj_bias),
+                       ("d_out_proj_weight", mha.out_proj.weight), ("d_out_proj_bias", mha.out_proj.bias)):
+            errs[key] = rel(q.grad.cpu().numpy(), ref[key], ref[key])
+        m = max(errs.values())
+        if world > 1:
+            t = torch.tensor([m], device=dev, dtype=torch.float64)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            m = float(t.item())
+        worst = max(worst, m)
+        cases.append({"case": c["name"], "shape": {k: c[k] for k in ("n", "e", "f", "d", "h")}, "graph": c["graph"],
+                      "max_rel": m, "ok": bool(m < PARITY_TOL)})
+    from ampnet_b200 import functional as F_
+    F_.check_status(sync=True)
+    return {"ok": all(c["ok"] for c in cases), "max_rel": worst, "tol": PARITY_TOL, "against": "oracle/numpy_oracle.py (fp64)",
+            "path": ("dist_amp_conv over %d ranks" % world) if world > 1 else "AMPConv module, 1 GPU", "cases": cases}
+
+
+# ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
 def algorithmic_bytes(spec, mode):
@@ -259,6 +325,7 @@ def run_ours(args):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    parity = None if args.no_parity_check else parity_check(dev, 1, 0, mode=args.mode if args.mode != "fp32" else "auto")
     x.requires_grad_(True)
     for _ in range(args.warmup):
         step(x, edge_index)
@@ -390,21 +457,28 @@ def run_ours(args):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if parity is not None:
+        line["parity_check"] = parity
     emit(line)
+    if parity is not None and not parity["ok"]:
+        raise SystemExit("parity check against the oracle failed: " + json.dumps(parity))
 
 
 def run_ours_partitioned(args, spec, world, rank, dev):
-    """N > 1: the SAME graph, destination-partitioned over the ranks (strong scaling); halo exchange of the referenced
-    K/V rows forward, return of the dK/dV halo rows and parameter-gradient all-reduce backward
-    (ampnet_b200/distributed.py)."""
+    """N > 1: the SAME graph, destination-partitioned over the ranks (strong scaling).  Exchange step = ring-phased pushes
+    over peer memory overlapped with the phases' compute (ampnet_b200/distributed.py, transport "peer"); NCCL carries one
+    barrier per step and the all-reduce of the parameter gradients."""
     import torch.distributed as dist
     from ampnet_b200 import AMPConv, _lib, distributed as D
+    from ampnet_b200 import functional as F_
     n, e, f, d, h = spec["n"], spec["e"], spec["f"], spec["d"], spec["h"]
+    parity = None if args.no_parity_check else parity_check(dev, world, rank)
+    D.close_engines()
     edge_index_np = make_problem(spec, args.graph, seed=0)            # identical on every rank
     ei_host = torch.from_numpy(edge_index_np).pin_memory()
     edge_index = ei_host.to(dev)
     pg = D.PartitionedGraph(edge_index, n, world, rank).build_plan()
-    pg.device_graph()
+    transport = D.default_transport(torch.empty(0, device=dev), pg)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     x = torch.randn((pg.n_local, f * d), generator=gen, device=dev)
     d_out = torch.randn((pg.n_local, f * d), generator=gen, device=dev)
@@ -419,7 +493,8 @@ def run_ours_partitioned(args, spec, world, rank, dev):
         for p in params:
             p.grad = None
         xin.grad = None
-        out = D.dist_amp_conv(xin, pg, mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight, mha.out_proj.bias, h)
+        out = D.dist_amp_conv(xin, pg, mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight, mha.out_proj.bias, h,
+                              key="bench")
         loss = torch.dot(out.detach().view(-1), d_out.view(-1)) if want_loss else None
         out.backward(d_out)
         return loss
@@ -449,9 +524,10 @@ def run_ours_partitioned(args, spec, world, rank, dev):
     if phases and rank == 0:
         sys.stderr.write("phase ms (rank 0): " + json.dumps({k: round(v, 2) for k, v in phases.items()}) + "\n")
 
-    # end to end: every step uploads this rank's rows of x from pinned memory (double-buffered: step i+1's upload overlaps
-    # step i's compute, ampnet_b200.loader.HostFeed), runs fwd + bwd with the collectives and reads the loss and the
-    # parameter gradients back
+    # end to end, same definition as the 1-GPU line: every step uploads this rank's rows of x and the edge_index from
+    # pinned memory (double-buffered, ampnet_b200.loader.HostFeed), rebuilds the rank's CSR views from the uploaded
+    # edges, runs fwd + bwd with the exchange and reads the loss and the parameter gradients back.  Static across steps:
+    # which destinations a rank owns and the halo plan (the index lists exchanged once per graph).
     from ampnet_b200.loader import HostFeed
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
     grads_host = [torch.empty_like(p, device="cpu").pin_memory() for p in params]
@@ -460,11 +536,20 @@ def run_ours_partitioned(args, spec, world, rank, dev):
     feed = HostFeed(dev)
 
     def e2e_run(k):
-        feed.submit(x_host)
+        feed.submit(x_host, ei_host)
         for i in range(k):
-            (x_dev,) = feed.get()
+            x_dev, ei_dev = feed.get()
             if i + 1 < k:
-                feed.submit(x_host)
+                feed.submit(x_host, ei_host)
+            if getattr(pg, "phase_graphs", None) is not None:
+                lei = torch.stack([pg.local_edge_index[0], ei_dev[1, pg.edge_ids] - pg.lo])   # destinations from the upload
+                pg.local_edge_index = lei.contiguous()
+                pg.phase_graphs = D.PhaseGraphs(pg, pg.phase_plan)
+                for eng in D._engines.values():
+                    if eng.pg is pg:
+                        eng.pgs = pg.phase_graphs
+            else:
+                pg.graph = None
             xin = x_dev.detach().requires_grad_(True)
             loss = step(xin, want_loss=True)
             loss_host.copy_(loss.detach(), non_blocking=True)
@@ -482,33 +567,56 @@ def run_ours_partitioned(args, spec, world, rank, dev):
     t = torch.tensor([ev0.elapsed_time(ev1) / e2e_steps], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
-    sizes = torch.tensor([x_host.numel() * 4, 4 + sum(p.numel() * 4 for p in params)], device=dev, dtype=torch.float64)
+    sizes = torch.tensor([x_host.numel() * 4 + ei_host.numel() * 8, 4 + sum(p.numel() * 4 for p in params)], device=dev,
+                         dtype=torch.float64)
     dist.all_reduce(sizes)
+    F_.check_status(sync=True)
+    mem = torch.tensor([torch.cuda.max_memory_allocated(dev) / 2 ** 30], device=dev, dtype=torch.float64)
+    dist.all_reduce(mem, op=dist.ReduceOp.MAX)
     if rank != 0:
         return
     pk = peaks()
+    # whole-step bounds: algorithmic FLOPs 14 F^2 d E + 24 F d^2 N against the sustained bf16 peak of all GPUs,
+    # exponentials 3 H F^2 E against the MUFU issue peak (16 / clk / SM at 1.965 GHz)
+    flops = 14.0 * f * f * d * e + 24.0 * f * d * d * n
+    exps = 3.0 * h * f * f * e
+    sec = ms_step * 1e-3
     line = {
-        "metric": METRIC, "value": e / (ms_step * 1e-3), "unit": "edges/s", "n_gpus": world, "steps": args.steps,
+        "metric": METRIC, "value": e / sec, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {spec['desc']} (N={n}, E={e}, F={f}, d={d}, H={h}), one AMPConv layer "
                                f"fwd+bwd, {args.graph} graph seed 7", "mode": "bf16",
                    "l2": "inputs larger than L2; no flush",
-                   "parallelism": f"dst-partitioned over {world} GPUs: halo exchange of referenced K|V rows (bf16 all-to-all), "
-                                  "dK|dV halo rows back to their owners (bf16 all-to-all, fixed-order adds), "
-                                  "all-reduce parameter gradients (NCCL)"},
-        "node_updates_per_s": n / (ms_step * 1e-3),
+                   "parallelism": f"dst-partitioned over {world} GPUs, transport {transport}: "
+                                  + ("ring-phased pushes of the referenced K|V rows into the peers' windows (CUDA IPC, copy "
+                                     "engines over NVLink) overlapped with the phases' attention; dK|dV blocks pushed back per "
+                                     "phase, fixed-order adds; NCCL: one barrier per step + all-reduce of the parameter gradients"
+                                     if transport == "peer" else
+                                     "halo exchange of referenced K|V rows (bf16 all-to-all), dK|dV halo rows back to their "
+                                     "owners (bf16 all-to-all, fixed-order adds), all-reduce parameter gradients (NCCL)")},
+        "node_updates_per_s": n / sec,
         "clocks": clocks.summary(),
         "e2e": {"value": e / (e2e_ms * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": int(sizes[0].item()),
                 "d2h_bytes_per_step": int(sizes[1].item()), "ms_per_step": e2e_ms, "steps": e2e_steps,
-                "includes": "every step: H2D of every rank's rows of x from pinned memory (double-buffered, step i+1's upload "
-                            "overlaps step i's compute, first upload exposed), fwd, bwd (with the collectives), D2H of loss "
-                            "and 4 param grads; the partitioned CSR is built once (static graph)"},
+                "includes": "every step, every rank: H2D of the rank's rows of x and of edge_index from pinned memory "
+                            "(double-buffered, step i+1's upload overlaps step i's compute, first upload exposed), rebuild of "
+                            "the rank's CSR views, fwd, bwd (with the exchange), D2H of loss and 4 param grads; static: the "
+                            "destination partition and the halo plan"},
         "gpu_launches": int(launches),
+        "max_memory_gib_per_gpu": float(mem.item()),
         "roofline": {"bound": "hbm", "kernel": "whole step (see the N=1 line for per-kernel numbers)", "achieved": None,
-                     "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": None, "traffic": None, "peak_source": pk["source"]},
+                     "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": None, "traffic": None, "peak_source": pk["source"],
+                     "tensor_frac": flops / sec / 1e12 / (pk["bf16_tflops"] * world),
+                     "mufu_frac": exps / sec / (148 * 1.965e9 * 16.0 * world)},
     }
+    if phases:
+        line["phase_ms_rank0"] = {k: round(v, 3) for k, v in phases.items()}
+    if parity is not None:
+        line["parity_check"] = parity
     emit(line)
+    if parity is not None and not parity["ok"]:
+        raise SystemExit("parity check against the oracle failed: " + json.dumps(parity))
 
 
 def profile_attention_kernels(conv, x, edge_index, d_out, mode, reps):
@@ -556,6 +664,7 @@ def main():
     ap.add_argument("--mode", default=os.environ.get("AMPNET_B200_BENCH_MODE", "bf16"))
     ap.add_argument("--cpu-sample-edges", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -291,6 +291,59 @@ AMPCONV_API int ampconv_attn_bwd_dkv_bf16_halo(const void* q, const void* k, con
 AMPCONV_API int ampconv_halo_add_bf16(const void* recv_bf16, const int32_t* tgt, const int32_t* rowptr, const int32_t* pos,
                           float* acc, int64_t n_tgt, int64_t row_elems, void* stream);
 
+/* Ring-phase variants of the three attention kernels (multi-GPU overlap, ampnet_b200/distributed.py).  The rank's edges are
+ * split by the OWNER of their source ("phase": 0 = own sources, t = the t-th owner in ring order); each phase has its own
+ * destination- / source-sorted views (ampconv_graph_build_bipartite over the phase's edges, compact source ids unchanged)
+ * and is one launch over the `n_work` nodes listed in `order`.  lse2 / delta are indexed by the phase's own slots.
+ *   fwd / dq : accumulate = 0 -> first phase executed (overwrites; destinations without an edge are zero-filled),
+ *              accumulate = 1 -> adds to agg / d_q (destinations without an edge in the phase are not in `order`);
+ *   dkv      : own sources (d_kv_halo NULL) -> d_kv_own fp32 [num_own*F, 128]; the phase owner's halo sources, compact ids
+ *              [halo_from, ...) -> bf16 rows d_kv_halo[(id - halo_from)*F, 128], the block that travels to that owner. */
+AMPCONV_API int ampconv_attn_fwd_bf16_phase(const void* q, const void* k, const void* v,
+                                const int32_t* dst_rowptr, const int32_t* dst_src, const float* inv_deg,
+                                const int32_t* order, int64_t n_work, int accumulate, float* agg, float* lse2,
+                                int64_t num_nodes, int64_t num_kv_nodes, int64_t num_edges,
+                                int F, int d, int H, void* workspace, size_t workspace_bytes, void* stream);
+AMPCONV_API int ampconv_attn_bwd_dq_bf16_phase(const void* q, const void* k, const void* v, const void* d_agg_bf16,
+                                   const float* lse2, const int32_t* dst_rowptr, const int32_t* dst_src,
+                                   const int32_t* order, int64_t n_work, int accumulate, float* d_q, float* delta,
+                                   int64_t num_nodes, int64_t num_kv_nodes, int64_t num_edges, int F, int d, int H,
+                                   void* workspace, size_t workspace_bytes, void* stream);
+AMPCONV_API int ampconv_attn_bwd_dkv_bf16_phase(const void* q, const void* k, const void* v, const void* d_agg_bf16,
+                                    const float* lse2, const float* delta, const int32_t* src_rowptr,
+                                    const int32_t* src_dst, const int32_t* src_pos, const int32_t* order,
+                                    int64_t n_work, float* d_kv_own, void* d_kv_halo, int64_t halo_from,
+                                    int64_t num_nodes, int64_t num_kv_nodes, int64_t num_edges, int F, int d, int H,
+                                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Peer memory over NVLink / NVSwitch (one process per GPU; csrc/peer.cu).  The exchange step of the partitioned path
+ * is not a collective: every rank maps its peers' receive windows (CUDA IPC) and PUSHES rows into them with
+ * stream-ordered device-to-device copies (copy engines: no SM is taken from the persistent attention kernels), then
+ * raises a flag word in the receiver's window; the receiver's compute stream waits for the flag right before the
+ * kernel that consumes the rows.
+ *   _alloc / _free : a zeroed cudaMalloc window (IPC handles need a whole allocation);
+ *   _export        : 64-byte IPC handle of a window; _open / _close: map / unmap a peer's window in this process;
+ *   _copy          : dst (local or peer) <- src, `bytes` bytes, on `stream`;
+ *   _ramp          : fills ramp[i] = i (the device-resident source of flag values); _signal: *peer_flag = value
+ *                    (value < ramp length), ordered after everything enqueued on `stream` before it;
+ *   _wait          : one-thread kernel on `stream` that returns when *flag == expected (ld.acquire.sys); after
+ *                    budget_seconds it records 601 | expected << 16 in the status word of `workspace` and gives up;
+ *   ampconv_gather_rows: dst[i, :] = src[idx[i], :] for rows of row_bytes (multiple of 16) bytes: packs the rows a
+ *                    receiver needs into one contiguous block.
+ * ------------------------------------------------------------------------------------------ */
+AMPCONV_API int ampconv_peer_alloc(size_t bytes, void** ptr);
+AMPCONV_API int ampconv_peer_free(void* ptr);
+AMPCONV_API int ampconv_peer_export(void* ptr, void* handle_out /* 64 bytes, host */);
+AMPCONV_API int ampconv_peer_open(const void* handle /* 64 bytes, host */, void** ptr);
+AMPCONV_API int ampconv_peer_close(void* ptr);
+AMPCONV_API int ampconv_peer_copy(void* dst, const void* src, size_t bytes, void* stream);
+AMPCONV_API int ampconv_peer_ramp(int32_t* ramp, int n, void* stream);
+AMPCONV_API int ampconv_peer_signal(int32_t* peer_flag, const int32_t* ramp, int32_t value, void* stream);
+AMPCONV_API int ampconv_peer_wait(const int32_t* flag, int32_t expected, void* workspace, double budget_seconds, void* stream);
+AMPCONV_API int ampconv_gather_rows(const void* src, const int64_t* idx, void* dst, int64_t n_rows, int64_t row_bytes,
+                        void* stream);
+
 /* Copies the status word of the last bf16 kernel that used `workspace` to the host (0 = ok, otherwise
  * the id of the pipeline wait that timed out).  Synchronises `stream`; meant for tests and debugging. */
 AMPCONV_API int ampconv_bf16_status(const void* workspace, int* status_host, void* stream);
