@@ -42,6 +42,7 @@ constexpr bool kPolyShare = true;      // a quarter of the exponentials are eval
 struct NodeSlot {
   int node, p_begin, p_end;
   float inv_deg;
+  int grp;     // head group of this work item (GROUPS == 2: head_dim 8, heads 4 grp .. 4 grp + 3 as padded head_dim-16 tiles)
 };
 
 // Reads a NodeSlot so that the compiler KNOWS the fields are warp-uniform (shfl from lane 0): the MMA warps' loop counters
@@ -52,6 +53,7 @@ __device__ __forceinline__ NodeSlot uniform_slot(const NodeSlot& s) {
   u.p_begin = __shfl_sync(0xffffffffu, s.p_begin, 0);
   u.p_end = __shfl_sync(0xffffffffu, s.p_end, 0);
   u.inv_deg = __shfl_sync(0xffffffffu, s.inv_deg, 0);
+  u.grp = __shfl_sync(0xffffffffu, s.grp, 0);
   return u;
 }
 
@@ -78,7 +80,11 @@ struct FwdSmem {
     if (!mbar_wait((bar), (parity))) AMP_FAIL(code);        \
   } while (0)
 
-template <int HD, bool PROF>
+// GROUPS == 2 serves head_dim 8 (embed 64, 8 heads: the ogbn-products shape) with the head_dim-16 pipeline: a work item is
+// (node, head group g); its tiles come through 4-D tensor maps whose box asks for 16 columns per head of which 8 exist (TMA
+// zero-fills the rest, umma.cuh: make_tensor_map_bf16_hd8), so Q_h K_h^T and P_h V_h see 8 real + 8 zero columns per head
+// and nothing padded ever exists in HBM; the epilogue writes the 8 real columns of every head to their true place.
+template <int HD, int GROUPS, bool PROF>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                      const __grid_constant__ CUtensorMap mapV, const int32_t* __restrict__ rowptr,
@@ -129,10 +135,12 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
     // Isolated nodes never enter the pipeline: the warp writes their zero rows directly.
     uint32_t qi = 0, ei = 0;
     for (;;) {
-      int node = -1, pb = 0, pe = 0;
+      int node = -1, pb = 0, pe = 0, grp = 0;
       if (lane == 0) {
         const int idx = atomicAdd(counter, 1);
-        node = idx < N ? (order ? order[idx] : idx) : -1;
+        const int ni = GROUPS == 1 ? idx : idx / GROUPS;
+        grp = GROUPS == 1 ? 0 : idx - ni * GROUPS;
+        node = ni < N ? (order ? order[ni] : ni) : -1;
         if (node >= 0) {
           pb = rowptr[node];
           pe = rowptr[node + 1];
@@ -141,8 +149,9 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       node = __shfl_sync(0xffffffffu, node, 0);
       pb = __shfl_sync(0xffffffffu, pb, 0);
       pe = __shfl_sync(0xffffffffu, pe, 0);
+      grp = __shfl_sync(0xffffffffu, grp, 0);
       if (node >= 0 && pe == pb) {
-        if (accumulate) continue;   // a later ring phase: the node's rows already hold the earlier phases' sum
+        if (accumulate || grp != 0) continue;   // later ring phase: rows hold the earlier sum; group 0 zero-fills the whole row
         float4* z = reinterpret_cast<float4*>(agg + (int64_t)node * F * kD);
         for (int i = lane; i < F * (kD / 4); i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         continue;
@@ -158,12 +167,14 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
           ns.p_begin = pb;
           ns.p_end = pe;
           ns.inv_deg = node >= 0 ? inv_deg[node] : 0.f;
+          ns.grp = grp;
           sm.slot[qb] = ns;
           if (node < 0) {
             mbar_arrive(&sm.q_full[qb]);
           } else {
             mbar_arrive_expect_tx(&sm.q_full[qb], kTileBytes);
-            tma_load_3d(sm.q[qb], &mapQ, &sm.q_full[qb], 0, 0, node);
+            if (GROUPS == 1) tma_load_3d(sm.q[qb], &mapQ, &sm.q_full[qb], 0, 0, node);
+            else tma_load_4d(sm.q[qb], &mapQ, &sm.q_full[qb], 0, 4 * grp, 0, node);
             int src_next = dst_src[pb];
             for (int p = pb; p < pe; ++p, ++ei) {
               const int src = src_next;
@@ -174,8 +185,13 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
                 break;
               }
               mbar_arrive_expect_tx(&sm.kv_full[st], 2 * kTileBytes);
-              tma_load_3d(sm.kv[st][0], &mapK, &sm.kv_full[st], 0, 0, src);
-              tma_load_3d(sm.kv[st][1], &mapV, &sm.kv_full[st], 0, 0, src);
+              if (GROUPS == 1) {
+                tma_load_3d(sm.kv[st][0], &mapK, &sm.kv_full[st], 0, 0, src);
+                tma_load_3d(sm.kv[st][1], &mapV, &sm.kv_full[st], 0, 0, src);
+              } else {
+                tma_load_4d(sm.kv[st][0], &mapK, &sm.kv_full[st], 0, 4 * grp, 0, src);
+                tma_load_4d(sm.kv[st][1], &mapV, &sm.kv_full[st], 0, 4 * grp, 0, src);
+              }
             }
           }
           ++qi;
@@ -270,11 +286,16 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       const uint32_t qb = qi & 1;
       AMP_WAIT(&sm.q_full[qb], (qi >> 1) & 1, 301);
       AMP_PHASE(8);
-      const NodeSlot ns = sm.slot[qb];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.q_empty[qb]);   // slot contents are in registers (8 of the 9 arrivals)
-      if (ns.node < 0) break;
-      for (int p = ns.p_begin; p < ns.p_end; ++p) {
+      // only the edge range lives in registers across the item loop (the softmax threads hold 192 values); node, inv_deg and
+      // grp are re-read from the slot in the node epilogue, so this warp releases the slot (q_empty) only after that
+      const int ns_node = sm.slot[qb].node, ns_pb = sm.slot[qb].p_begin, ns_pe = sm.slot[qb].p_end;
+      const int ns_grp = GROUPS == 1 ? 0 : sm.slot[qb].grp;
+      if (ns_node < 0) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.q_empty[qb]);
+        break;
+      }
+      for (int p = ns_pb; p < ns_pe; ++p) {
 #pragma unroll
         for (int hl = 0; hl < HL; ++hl) {
           const int h = 2 * hl + b;
@@ -340,7 +361,7 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&sm.p_full[b]);
-          if (row_ok) lse2[((int64_t)p * H + h) * ((F + 3) & ~3) + row] = m + __log2f(l);
+          if (row_ok) lse2[((int64_t)p * (H * GROUPS) + ns_grp * H + h) * ((F + 3) & ~3) + row] = m + __log2f(l);
           AMP_PHASE(5);
           ++c;
         }
@@ -364,13 +385,20 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.o_empty[par]);
+        NodeSlot ns;
+        ns.node = sm.slot[qb].node;
+        ns.inv_deg = sm.slot[qb].inv_deg;
+        ns.grp = GROUPS == 1 ? 0 : sm.slot[qb].grp;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.q_empty[qb]);   // slot contents are in registers (8 of the 11 arrivals)
         if (row_ok) {
           float* dst = agg + ((int64_t)ns.node * F + row) * kD;
 #pragma unroll
           for (int hl = 0; hl < HL; ++hl) {
-            float4* o4 = reinterpret_cast<float4*>(dst + (2 * hl + b) * HD);
+            // GROUPS == 2: the 8 real columns of padded head 2 hl + b go to columns [32 grp + 8 (2 hl + b), + 8)
+            float4* o4 = reinterpret_cast<float4*>(dst + (GROUPS == 1 ? (2 * hl + b) * HD : 32 * ns.grp + 8 * (2 * hl + b)));
 #pragma unroll
-            for (int x = 0; x < HD; x += 4) {
+            for (int x = 0; x < (GROUPS == 1 ? HD : 8); x += 4) {
               float4 r = make_float4(__uint_as_float(o[hl][x]) * ns.inv_deg, __uint_as_float(o[hl][x + 1]) * ns.inv_deg,
                                      __uint_as_float(o[hl][x + 2]) * ns.inv_deg, __uint_as_float(o[hl][x + 3]) * ns.inv_deg);
               if (accumulate) {   // ring phases (multi-GPU): the mean is a sum over all phases' edges, inv_deg is the full one
@@ -405,7 +433,7 @@ using namespace ampconv;
 extern "C" int ampconv_attn_bf16_supported(int F, int d, int H) {
   if (d != kD || H <= 0 || d % H) return 0;
   const int hd = d / H;
-  return (hd == 16 || hd == 32) && F >= 1 && F <= 128;
+  return (hd == 16 || hd == 32 || hd == 8) && F >= 1 && F <= 128;   // hd 8: two head groups through zero-padding TMA boxes
 }
 
 static int attn_fwd_bf16_impl(const void* q, const void* k, const void* v,
@@ -423,26 +451,33 @@ static int attn_fwd_bf16_impl(const void* q, const void* k, const void* v,
   if (workspace_bytes < 256) return AMPCONV_ERR_WORKSPACE;
   cudaStream_t stream = as_stream(stream_);
   CUtensorMap mq, mk, mv;
-  if (!make_tensor_map_bf16_3d(&mq, q, kD, F, N, kD, 128) || !make_tensor_map_bf16_3d(&mk, k, kD, F, N_kv, kD, 128) ||
-      !make_tensor_map_bf16_3d(&mv, v, kD, F, N_kv, kD, 128))
+  const int hd = d / H;
+  if (hd == 8) {
+    if (!make_tensor_map_bf16_hd8(&mq, q, F, N) || !make_tensor_map_bf16_hd8(&mk, k, F, N_kv) || !make_tensor_map_bf16_hd8(&mv, v, F, N_kv))
+      return AMPCONV_ERR_CUDA;
+  } else if (!make_tensor_map_bf16_3d(&mq, q, kD, F, N, kD, 128) || !make_tensor_map_bf16_3d(&mk, k, kD, F, N_kv, kD, 128) ||
+             !make_tensor_map_bf16_3d(&mv, v, kD, F, N_kv, kD, 128)) {
     return AMPCONV_ERR_CUDA;
+  }
   int* counter = reinterpret_cast<int*>(workspace);
   int* status = counter + 1;
   AMPCONV_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(int), stream));   // the status word (counter + 1) is the caller's: zeroed once per layer call
   const size_t smem = sizeof(FwdSmem) + 1024;
-  const int grid = (int)(n_work < sm_count() ? n_work : sm_count());
-  const int hd = d / H;
-#define AMP_LAUNCH_FWD(HDV, PROFV)                                                                                    \
+  const int64_t items = n_work * (hd == 8 ? 2 : 1);
+  const int grid = (int)(items < sm_count() ? items : sm_count());
+#define AMP_LAUNCH_FWD(HDV, GRP, PROFV)                                                                                    \
   do {                                                                                                                \
-    AMPCONV_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_bf16_kernel<HDV, PROFV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+    AMPCONV_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_bf16_kernel<HDV, GRP, PROFV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                           (int)smem));                                                                \
-    attn_fwd_bf16_kernel<HDV, PROFV><<<grid, kFwdThreads, smem, stream>>>(mq, mk, mv, dst_rowptr, dst_src, inv_deg, order, \
+    attn_fwd_bf16_kernel<HDV, GRP, PROFV><<<grid, kFwdThreads, smem, stream>>>(mq, mk, mv, dst_rowptr, dst_src, inv_deg, order, \
                                                                          counter, status, agg, lse2, (int)n_work, F, accumulate, prof);  \
   } while (0)
-  if (hd == 16) {
-    if (prof) AMP_LAUNCH_FWD(16, true); else AMP_LAUNCH_FWD(16, false);
+  if (hd == 8) {
+    AMP_LAUNCH_FWD(16, 2, false);
+  } else if (hd == 16) {
+    if (prof) AMP_LAUNCH_FWD(16, 1, true); else AMP_LAUNCH_FWD(16, 1, false);
   } else {
-    if (prof) AMP_LAUNCH_FWD(32, true); else AMP_LAUNCH_FWD(32, false);
+    if (prof) AMP_LAUNCH_FWD(32, 1, true); else AMP_LAUNCH_FWD(32, 1, false);
   }
 #undef AMP_LAUNCH_FWD
   AMPCONV_CHECK_LAUNCH();

@@ -57,6 +57,7 @@ constexpr bool kPolyShareDq = false, kPolyShareDkv = false;
 
 struct NodeSlot {
   int node, e_begin, e_end;
+  int grp;     // head group of this work item (GROUPS == 2: head_dim 8 as zero-padded head_dim-16 tiles, see attn_bf16.cu)
 };
 // Reads a NodeSlot so that the compiler KNOWS the fields are warp-uniform (shfl from lane 0): loop counters and the
 // descriptor / TMEM address arithmetic derived from them can then live in uniform registers, and a tcgen05.mma
@@ -66,6 +67,7 @@ __device__ __forceinline__ NodeSlot uniform_slot(const NodeSlot& s) {
   u.node = __shfl_sync(0xffffffffu, s.node, 0);
   u.e_begin = __shfl_sync(0xffffffffu, s.e_begin, 0);
   u.e_end = __shfl_sync(0xffffffffu, s.e_end, 0);
+  u.grp = __shfl_sync(0xffffffffu, s.grp, 0);
   return u;
 }
 struct TrueTag { static constexpr bool value = true; };
@@ -130,7 +132,10 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
 // own0/own1: tensor maps of the per-node tiles, oth0/oth1: of the per-edge tiles.
 // rowptr/nbr: CSR of the pass (by destination for MODE_DQ, by source for MODE_DKV); slot_of[e] = position of
 // edge e in the statistics arrays (NULL: identity).  d_qkv: fp32 [rows, out_ld].
-template <int HD, int MODE, int NH, bool PROF>
+// GROUPS == 2 (head_dim 8): a work item is (node, head group); tiles arrive zero-padded to 16 columns per head through the
+// 4-D tensor maps of umma.cuh (nothing padded in HBM), statistics rows are those of the group's four heads, and the epilogues
+// write the 8 real columns of every head to their true place.
+template <int HD, int MODE, int NH, int GROUPS, bool PROF>
 __global__ void __launch_bounds__(threads_of(MODE), 1)
 attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_constant__ CUtensorMap own1,
                      const __grid_constant__ CUtensorMap oth0, const __grid_constant__ CUtensorMap oth1,
@@ -141,7 +146,8 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
                      uint16_t* __restrict__ halo_bf16, int halo_from, int accumulate, long long* __restrict__ prof) {
   using Smem = BwdSmem<MODE>;
   constexpr int NS = Smem::NS;
-  constexpr int H = kD / HD;
+  constexpr int H = kD / HD;          // heads of a work item
+  constexpr int HT = H * GROUPS;      // heads of the layer (row count of an edge's statistics block)
   extern __shared__ uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sm32 = smem_base_opaque(&sm);   // shared-space address of sm, held in a register by the hot loops
@@ -209,10 +215,12 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
     else asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     uint32_t qi = 0, ei = 0;
     for (;;) {
-      int node = -1, eb = 0, ee = 0;
+      int node = -1, eb = 0, ee = 0, grp = 0;
       if (lane == 0) {
         const int idx = atomicAdd(counter, 1);
-        node = idx < N ? (order ? order[idx] : idx) : -1;
+        const int ni = GROUPS == 1 ? idx : idx / GROUPS;
+        grp = GROUPS == 1 ? 0 : idx - ni * GROUPS;
+        node = ni < N ? (order ? order[ni] : ni) : -1;
         if (node >= 0) {
           eb = rowptr[node];
           ee = rowptr[node + 1];
@@ -221,10 +229,11 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       node = __shfl_sync(0xffffffffu, node, 0);
       eb = __shfl_sync(0xffffffffu, eb, 0);
       ee = __shfl_sync(0xffffffffu, ee, 0);
+      grp = __shfl_sync(0xffffffffu, grp, 0);
       if (node >= 0 && ee == eb) {
         // node without edges in this pass: its gradient rows are zero (halo sources always have an edge)
         if (halo_bf16 != nullptr && node >= halo_from) continue;
-        if (accumulate) continue;   // a later ring phase: the node's rows already hold the earlier phases' sum
+        if (accumulate || grp != 0) continue;   // later ring phase: rows hold the earlier sum; group 0 zero-fills whole rows
         const int nblk = MODE == MODE_DQ ? 1 : 2;
         for (int i = lane; i < F * nblk * (kD / 4); i += 32) {
           const int r = i / (nblk * (kD / 4)), rem = i - r * (nblk * (kD / 4));
@@ -244,13 +253,19 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
           ns.node = node;
           ns.e_begin = eb;
           ns.e_end = ee;
+          ns.grp = grp;
           sm.slot[qb] = ns;
           if (node < 0) {
             mbar_arrive(&sm.own_full[qb]);
           } else {
             mbar_arrive_expect_tx(&sm.own_full[qb], 2 * kTileBytes);
-            tma_load_3d(sm.own[qb][0], &own0, &sm.own_full[qb], 0, 0, node);
-            tma_load_3d(sm.own[qb][1], &own1, &sm.own_full[qb], 0, 0, node);
+            if (GROUPS == 1) {
+              tma_load_3d(sm.own[qb][0], &own0, &sm.own_full[qb], 0, 0, node);
+              tma_load_3d(sm.own[qb][1], &own1, &sm.own_full[qb], 0, 0, node);
+            } else {
+              tma_load_4d(sm.own[qb][0], &own0, &sm.own_full[qb], 0, 4 * grp, 0, node);
+              tma_load_4d(sm.own[qb][1], &own1, &sm.own_full[qb], 0, 4 * grp, 0, node);
+            }
             int nb_next = nbr[eb];
             for (int e = eb; e < ee; ++e, ++ei) {
               const int nb = nb_next;
@@ -263,14 +278,19 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
               if (MODE == MODE_DKV) {
                 const int64_t sl = slot_of ? slot_of[e] : e;
                 mbar_arrive_expect_tx(&sm.edge_full[st], 2 * kTileBytes + 2 * stat_bytes);
-                bulk_load(sm.stat[st][0], lse2 + sl * H * Fs, stat_bytes, &sm.edge_full[st]);
-                bulk_load(sm.stat[st][1], delta + sl * H * Fs, stat_bytes, &sm.edge_full[st]);
+                bulk_load(sm.stat[st][0], lse2 + (sl * HT + grp * H) * Fs, stat_bytes, &sm.edge_full[st]);
+                bulk_load(sm.stat[st][1], delta + (sl * HT + grp * H) * Fs, stat_bytes, &sm.edge_full[st]);
               } else {
                 mbar_arrive_expect_tx(&sm.edge_full[st], 2 * kTileBytes + stat_bytes);
-                bulk_load(sm.stat[st][0], lse2 + (int64_t)e * H * Fs, stat_bytes, &sm.edge_full[st]);
+                bulk_load(sm.stat[st][0], lse2 + ((int64_t)e * HT + grp * H) * Fs, stat_bytes, &sm.edge_full[st]);
               }
-              tma_load_3d(sm.edge[st][0], &oth0, &sm.edge_full[st], 0, 0, nb);
-              tma_load_3d(sm.edge[st][1], &oth1, &sm.edge_full[st], 0, 0, nb);
+              if (GROUPS == 1) {
+                tma_load_3d(sm.edge[st][0], &oth0, &sm.edge_full[st], 0, 0, nb);
+                tma_load_3d(sm.edge[st][1], &oth1, &sm.edge_full[st], 0, 0, nb);
+              } else {
+                tma_load_4d(sm.edge[st][0], &oth0, &sm.edge_full[st], 0, 4 * grp, 0, nb);
+                tma_load_4d(sm.edge[st][1], &oth1, &sm.edge_full[st], 0, 4 * grp, 0, nb);
+              }
             }
           }
           ++qi;
@@ -420,7 +440,9 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.own_empty[qb]);
         if (ns.node < 0) break;
-        float* delta_row = delta + (int64_t)ns.e_begin * H * Fs + row;   // statistics rows of a node's items are consecutive
+        // statistics rows of an edge's items are consecutive; with two head groups an edge's block has HT rows, this item's
+        // group owns H of them
+        float* delta_row = delta + ((int64_t)ns.e_begin * HT + ns.grp * H) * Fs + row;
         for (int e = ns.e_begin; e < ns.e_end; ++e) {
 #pragma unroll 1
           for (int h = 0; h < H; ++h, ++item) {
@@ -448,6 +470,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
             if (row_ok) delta_row[0] = dsum;
             delta_row += Fs;
           }
+          if (GROUPS > 1) delta_row += (HT - H) * Fs;
         }
         // node end: all consumer MMAs of the node have landed in the dQ accumulator
         AMP_XWAIT(2, SM_OFF(acc_full), qi & 1, 404);
@@ -465,14 +488,16 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
             sts_f32(racc + (16 * c4 + x) * 512, 0.f);
           }
           if (row_ok) {
+            // GROUPS == 2 (HD == 16): TMEM columns [16 c4, 16 c4 + 8) are the real columns of padded head c4
+            float* oc = GROUPS == 1 ? o + 16 * c4 : o + 32 * ns.grp + 8 * c4;
 #pragma unroll
-            for (int x = 0; x < 16; x += 4) {
+            for (int x = 0; x < (GROUPS == 1 ? 16 : 8); x += 4) {
               float4 r = make_float4(v[x], v[x + 1], v[x + 2], v[x + 3]);
               if (accumulate) {   // ring phases (multi-GPU): dQ is a sum over all phases' edges
-                const float4 pr = *reinterpret_cast<const float4*>(o + 16 * c4 + x);
+                const float4 pr = *reinterpret_cast<const float4*>(oc + x);
                 r.x += pr.x; r.y += pr.y; r.z += pr.z; r.w += pr.w;
               }
-              *reinterpret_cast<float4*>(o + 16 * c4 + x) = r;
+              *reinterpret_cast<float4*>(oc + x) = r;
             }
           }
         }
@@ -672,23 +697,47 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
         if (row_ok) {
           const bool is_dv = j4 < 2;
           const float sc = is_dv ? out_scale1 : out_scale0;
-          if (halo_bf16 != nullptr && ns.node >= halo_from) {
-            // halo source (multi-GPU): this partial row travels to its owner, written as bf16 [node - halo_from][row][out_ld]
-            uint4* o = reinterpret_cast<uint4*>(halo_bf16 + ((int64_t)(ns.node - halo_from) * F + row) * out_ld +
-                                                (is_dv ? out_c1 : out_c0) + 32 * (j4 & 1));
-#pragma unroll
-            for (int x = 0; x < 32; x += 8)
-              o[x >> 3] = make_uint4(pack_bf16x2(__uint_as_float(a[x]) * sc, __uint_as_float(a[x + 1]) * sc),
-                                     pack_bf16x2(__uint_as_float(a[x + 2]) * sc, __uint_as_float(a[x + 3]) * sc),
-                                     pack_bf16x2(__uint_as_float(a[x + 4]) * sc, __uint_as_float(a[x + 5]) * sc),
-                                     pack_bf16x2(__uint_as_float(a[x + 6]) * sc, __uint_as_float(a[x + 7]) * sc));
-          } else {
-            float4* o = reinterpret_cast<float4*>(d_qkv + ((int64_t)ns.node * F + row) * out_ld +
+          if (GROUPS == 1) {
+            if (halo_bf16 != nullptr && ns.node >= halo_from) {
+              // halo source (multi-GPU): this partial row travels to its owner, written as bf16 [node - halo_from][row][out_ld]
+              uint4* o = reinterpret_cast<uint4*>(halo_bf16 + ((int64_t)(ns.node - halo_from) * F + row) * out_ld +
                                                   (is_dv ? out_c1 : out_c0) + 32 * (j4 & 1));
 #pragma unroll
-            for (int x = 0; x < 32; x += 4)
-              o[x >> 2] = make_float4(__uint_as_float(a[x]) * sc, __uint_as_float(a[x + 1]) * sc,
-                                      __uint_as_float(a[x + 2]) * sc, __uint_as_float(a[x + 3]) * sc);
+              for (int x = 0; x < 32; x += 8)
+                o[x >> 3] = make_uint4(pack_bf16x2(__uint_as_float(a[x]) * sc, __uint_as_float(a[x + 1]) * sc),
+                                       pack_bf16x2(__uint_as_float(a[x + 2]) * sc, __uint_as_float(a[x + 3]) * sc),
+                                       pack_bf16x2(__uint_as_float(a[x + 4]) * sc, __uint_as_float(a[x + 5]) * sc),
+                                       pack_bf16x2(__uint_as_float(a[x + 6]) * sc, __uint_as_float(a[x + 7]) * sc));
+            } else {
+              float4* o = reinterpret_cast<float4*>(d_qkv + ((int64_t)ns.node * F + row) * out_ld +
+                                                    (is_dv ? out_c1 : out_c0) + 32 * (j4 & 1));
+#pragma unroll
+              for (int x = 0; x < 32; x += 4)
+                o[x >> 2] = make_float4(__uint_as_float(a[x]) * sc, __uint_as_float(a[x + 1]) * sc,
+                                        __uint_as_float(a[x + 2]) * sc, __uint_as_float(a[x + 3]) * sc);
+            }
+          } else {
+            // head_dim 8: this warp's 32 accumulator columns are padded heads 2 (j4 & 1) and 2 (j4 & 1) + 1 (16 columns each,
+            // 8 real); head lh of group grp lives in columns [32 grp + 8 lh, + 8) of the 64-wide dK (dV) row
+            const int ns_grp = ns.grp;   // (the slot itself may already hold the next node: this warp released it at the top)
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int col = (is_dv ? out_c1 : out_c0) + 32 * ns_grp + 8 * (2 * (int)(j4 & 1) + u);
+              const uint32_t* au = a + 16 * u;
+              if (halo_bf16 != nullptr && ns.node >= halo_from) {
+                *reinterpret_cast<uint4*>(halo_bf16 + ((int64_t)(ns.node - halo_from) * F + row) * out_ld + col) =
+                    make_uint4(pack_bf16x2(__uint_as_float(au[0]) * sc, __uint_as_float(au[1]) * sc),
+                               pack_bf16x2(__uint_as_float(au[2]) * sc, __uint_as_float(au[3]) * sc),
+                               pack_bf16x2(__uint_as_float(au[4]) * sc, __uint_as_float(au[5]) * sc),
+                               pack_bf16x2(__uint_as_float(au[6]) * sc, __uint_as_float(au[7]) * sc));
+              } else {
+                float4* o = reinterpret_cast<float4*>(d_qkv + ((int64_t)ns.node * F + row) * out_ld + col);
+                o[0] = make_float4(__uint_as_float(au[0]) * sc, __uint_as_float(au[1]) * sc, __uint_as_float(au[2]) * sc,
+                                   __uint_as_float(au[3]) * sc);
+                o[1] = make_float4(__uint_as_float(au[4]) * sc, __uint_as_float(au[5]) * sc, __uint_as_float(au[6]) * sc,
+                                   __uint_as_float(au[7]) * sc);
+              }
+            }
           }
         }
       }
@@ -712,23 +761,24 @@ fail:
 
 long long* g_bwd_prof = nullptr;   // debug: set through ampconv_debug_set_bwd_profile
 
-template <int HD, int MODE>
+template <int HD, int MODE, int GROUPS>
 int launch_bwd(const CUtensorMap& own0, const CUtensorMap& own1, const CUtensorMap& oth0, const CUtensorMap& oth1,
                const int32_t* rowptr, const int32_t* nbr, const int32_t* slot_of, const int32_t* order, const float* lse2,
                float* delta, float* d_qkv, int* counter, int* status, int N, int F, float s0, float s1, int out_ld, int out_c0,
                int out_c1, uint16_t* halo_bf16, int halo_from, int accumulate, cudaStream_t stream) {
   const size_t smem = sizeof(BwdSmem<MODE>) + 1024;
-  const int grid = N < sm_count() ? N : sm_count();
+  const int items = N * GROUPS;
+  const int grid = items < sm_count() ? items : sm_count();
   long long* prof = g_bwd_prof;
 #define AMP_LAUNCH_BWD(NH_, PROF_, prof_)                                                                                          \
   do {                                                                                                                           \
-    AMPCONV_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_bf16_kernel<HD, MODE, NH_, PROF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+    AMPCONV_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_bf16_kernel<HD, MODE, NH_, GROUPS, PROF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                           (int)smem));                                                                           \
-    attn_bwd_bf16_kernel<HD, MODE, NH_, PROF_><<<grid, threads_of(MODE), smem, stream>>>(                                         \
+    attn_bwd_bf16_kernel<HD, MODE, NH_, GROUPS, PROF_><<<grid, threads_of(MODE), smem, stream>>>(                                         \
         own0, own1, oth0, oth1, rowptr, nbr, slot_of, order, lse2, delta, d_qkv, counter, status, N, F, s0, s1, out_ld, out_c0,   \
         out_c1, halo_bf16, halo_from, accumulate, prof_);                                                                                  \
   } while (0)
-  if (prof) {
+  if (prof && GROUPS == 1) {
     if (F > 64) AMP_LAUNCH_BWD(2, true, prof);
     else AMP_LAUNCH_BWD(1, true, prof);
   } else {
@@ -766,9 +816,14 @@ static int bwd_common(int mode, const void* q, const void* k, const void* v, con
   cudaStream_t stream = as_stream(stream_);
   CUtensorMap mq, mk, mv, mg;
   const int64_t nd = N_dst > 0 ? N_dst : 1, nk = N_kv > 0 ? N_kv : 1;
-  if (!make_tensor_map_bf16_3d(&mq, q, kD, F, nd, kD, 128) || !make_tensor_map_bf16_3d(&mk, k, kD, F, nk, kD, 128) ||
-      !make_tensor_map_bf16_3d(&mv, v, kD, F, nk, kD, 128) || !make_tensor_map_bf16_3d(&mg, d_agg_bf16, kD, F, nd, kD, 128))
+  if (d / H == 8) {
+    if (!make_tensor_map_bf16_hd8(&mq, q, F, nd) || !make_tensor_map_bf16_hd8(&mk, k, F, nk) ||
+        !make_tensor_map_bf16_hd8(&mv, v, F, nk) || !make_tensor_map_bf16_hd8(&mg, d_agg_bf16, F, nd))
+      return AMPCONV_ERR_CUDA;
+  } else if (!make_tensor_map_bf16_3d(&mq, q, kD, F, nd, kD, 128) || !make_tensor_map_bf16_3d(&mk, k, kD, F, nk, kD, 128) ||
+             !make_tensor_map_bf16_3d(&mv, v, kD, F, nk, kD, 128) || !make_tensor_map_bf16_3d(&mg, d_agg_bf16, kD, F, nd, kD, 128)) {
     return AMPCONV_ERR_CUDA;
+  }
   int* counter = reinterpret_cast<int*>(workspace) + (mode == MODE_DQ ? 2 : 4);
   int* status = reinterpret_cast<int*>(workspace) + 1;
   AMPCONV_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(int), stream));
@@ -777,17 +832,23 @@ static int bwd_common(int mode, const void* q, const void* k, const void* v, con
   const float ln2 = 0.6931471805599453f;
   if (mode == MODE_DQ) {
     // dQ = hd^-1/2 * (dS K)
+    if (hd == 8)
+      return launch_bwd<16, MODE_DQ, 2>(mq, mg, mk, mv, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)n_work, F,
+                                       inv_sqrt_hd, 0.f, out_ld, out_c0, out_c1, nullptr, 0, accumulate, stream);
     if (hd == 16)
-      return launch_bwd<16, MODE_DQ>(mq, mg, mk, mv, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)n_work, F,
+      return launch_bwd<16, MODE_DQ, 1>(mq, mg, mk, mv, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)n_work, F,
                                     inv_sqrt_hd, 0.f, out_ld, out_c0, out_c1, nullptr, 0, accumulate, stream);
-    return launch_bwd<32, MODE_DQ>(mq, mg, mk, mv, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)n_work, F,
+    return launch_bwd<32, MODE_DQ, 1>(mq, mg, mk, mv, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)n_work, F,
                                   inv_sqrt_hd, 0.f, out_ld, out_c0, out_c1, nullptr, 0, accumulate, stream);
   }
   // dK = hd^-1/2 * dS^T Q = ln2 * dS^T Q'  (Q' = Q * log2e / sqrt(hd)),  dV = P^T dO
+  if (hd == 8)
+    return launch_bwd<16, MODE_DKV, 2>(mk, mv, mq, mg, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)n_work, F,
+                                      ln2, 1.f, out_ld, out_c0, out_c1, reinterpret_cast<uint16_t*>(halo_bf16), (int)halo_from, 0, stream);
   if (hd == 16)
-    return launch_bwd<16, MODE_DKV>(mk, mv, mq, mg, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)n_work, F,
+    return launch_bwd<16, MODE_DKV, 1>(mk, mv, mq, mg, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)n_work, F,
                                    ln2, 1.f, out_ld, out_c0, out_c1, reinterpret_cast<uint16_t*>(halo_bf16), (int)halo_from, 0, stream);
-  return launch_bwd<32, MODE_DKV>(mk, mv, mq, mg, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)n_work, F, ln2,
+  return launch_bwd<32, MODE_DKV, 1>(mk, mv, mq, mg, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)n_work, F, ln2,
                                  1.f, out_ld, out_c0, out_c1, reinterpret_cast<uint16_t*>(halo_bf16), (int)halo_from, 0, stream);
 }
 

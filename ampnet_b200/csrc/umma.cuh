@@ -148,6 +148,12 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
@@ -409,6 +415,24 @@ inline bool make_tensor_map_bf16_3d(CUtensorMap* map, const void* base, uint64_t
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// head_dim 8 (embed 64, 8 heads) as padded head_dim-16 tiles WITHOUT padded copies in HBM: the bf16 tensor [N][F][64] is
+// described as 4-D {8 columns of a head, 8 heads, F tokens, N nodes}; a box {16, 4, 128, 1} at head coordinate 4g asks for 16
+// columns per head, of which only 8 exist -- TMA zero-fills the out-of-bounds half.  The shared-memory tile is then the 128 x
+// (4 heads x (8 real + 8 zero columns)) K-major tile the head_dim-16 kernels consume (dense in traversal order: 128 bytes per
+// token row, 128B swizzle on the linear address); only the real bytes travel.
+inline bool make_tensor_map_bf16_hd8(CUtensorMap* map, const void* base, uint64_t F, uint64_t N) {
+  PFN_tensorMapEncodeTiled enc = tensor_map_encoder();
+  if (!enc) return false;
+  cuuint64_t dims[4] = {8, 8, F, N};
+  cuuint64_t strides[3] = {16, 128, F * 128};
+  cuuint32_t box[4] = {16, 4, 128, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }

@@ -833,7 +833,7 @@ def dist_amp_conv(x_local, pg, w_in, b_in, w_out, b_out, num_heads, group=None, 
 
     if key is None:
         key = ("param", w_in.data_ptr())
-    if F_.bf16_supported(f, d, num_heads):
+    if F_.bf16_supported(f, d, num_heads) and not F_.bf16_grouped_supported(f, d, num_heads):
         return layer(x_local, w_in, b_in, w_out, b_out, num_heads, key)
     if F_.bf16_grouped_supported(f, d, num_heads):
         # head_dim 8 without the native kernels: two 4-head passes over zero-padded heads, composed by autograd

@@ -21,11 +21,16 @@ def bf16_supported(f, d, h):
     return bool(lib.ampconv_attn_bf16_supported(int(f), int(d), int(h)))
 
 
-HD8_GROUPED = True   # head_dim 8 (embed 64, 8 heads: the ogbn-products shape) on the tensor-core kernels, see _forward_bf16_hd8
+import os
+
+# head_dim 8 (embed 64, 8 heads: the ogbn-products shape) is native to the tcgen05 kernels (zero-padding TMA boxes, one launch
+# per pass).  AMPNET_B200_HD8=grouped selects the round-1 head-group decomposition instead (two launches over padded copies;
+# kept for A/B timing only).
+HD8_GROUPED = os.environ.get("AMPNET_B200_HD8", "") == "grouped"
 
 
 def bf16_grouped_supported(f, d, h):
-    """embed 64 with 8 heads of 8: served by the head_dim-16 kernels as two groups of four zero-padded heads."""
+    """embed 64 with 8 heads of 8 through the head-group decomposition (two groups of four zero-padded heads)."""
     return HD8_GROUPED and d == 64 and h == 8 and bf16_supported(f, 64, 4)
 
 
@@ -35,10 +40,10 @@ def resolve_mode(mode, f, d, h):
         raise ValueError(f"unknown mode {mode!r}; available: {MODES}")
     if mode == "fp32":
         return mode
-    if bf16_supported(f, d, h):
-        return "bf16"
     if bf16_grouped_supported(f, d, h):
         return "bf16g"
+    if bf16_supported(f, d, h):
+        return "bf16"
     if mode == "bf16":
         raise ValueError(f"mode='bf16' (tcgen05 kernels) does not cover F={f}, embed_dim={d}, num_heads={h}; "
                          "use mode='auto' or 'fp32'")

@@ -69,8 +69,8 @@ def test_mode_resolution_per_baseline_config():
     from ampnet_b200 import functional as F_
     assert F_.resolve_mode("auto", 128, 64, 4) == "bf16"        # C4: ogbn-arxiv token shape, head_dim 16
     assert F_.resolve_mode("bf16", 20, 64, 2) == "bf16"         # head_dim 32
-    assert F_.resolve_mode("auto", 100, 64, 8) == "bf16g"       # C5: ogbn-products token shape, head-group decomposition
-    assert F_.resolve_mode("bf16", 100, 64, 8) == "bf16g"
+    assert F_.resolve_mode("auto", 100, 64, 8) == "bf16"        # C5: ogbn-products token shape, head_dim 8 native (padding TMA boxes)
+    assert F_.resolve_mode("bf16", 100, 64, 8) == "bf16"
     assert F_.resolve_mode("fp32", 100, 64, 8) == "fp32"        # the strict family is always available
     assert F_.resolve_mode("auto", 20, 128, 4) == "fp32"        # C2: embed 128 is outside the tensor-core family
     assert F_.resolve_mode("auto", 1433, 12, 3) == "fp32"       # C1
