@@ -7,7 +7,8 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libampconv.so")
+# AMPNET_B200_LIB: an alternative build of the same library (kernel A/B experiments, tools/); the product is libampconv.so
+LIB_PATH = os.environ.get("AMPNET_B200_LIB") or os.path.join(_HERE, "libampconv.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "ampconv.h")
 
 _lib = None

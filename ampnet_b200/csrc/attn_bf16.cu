@@ -81,9 +81,10 @@ struct FwdSmem {
   } while (0)
 
 // GROUPS == 2 serves head_dim 8 (embed 64, 8 heads: the ogbn-products shape) with the head_dim-16 pipeline: a work item is
-// (node, head group g); its tiles come through 4-D tensor maps whose box asks for 16 columns per head of which 8 exist (TMA
-// zero-fills the rest, umma.cuh: make_tensor_map_bf16_hd8), so Q_h K_h^T and P_h V_h see 8 real + 8 zero columns per head
-// and nothing padded ever exists in HBM; the epilogue writes the 8 real columns of every head to their true place.
+// (node, head group g); the producer warp builds its tiles with cp.async (umma.cuh: load_padded_tile): the 8 real columns of
+// every head land in the first half of a 16-column slot whose second half stays zero, so Q_h K_h^T and P_h V_h see 8 real +
+// 8 zero columns per head and nothing padded ever exists in HBM; the epilogue writes the 8 real columns of every head to
+// their true place.
 template <int HD, int GROUPS, bool PROF>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
@@ -91,6 +92,7 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
                      const int32_t* __restrict__ dst_src, const float* __restrict__ inv_deg,
                      const int32_t* __restrict__ order, int* __restrict__ counter, int* __restrict__ status,
                      float* __restrict__ agg, float* __restrict__ lse2, int N, int F, int accumulate,
+                     const uint8_t* __restrict__ gq, const uint8_t* __restrict__ gk, const uint8_t* __restrict__ gv,
                      long long* __restrict__ prof) {
   constexpr int H = kD / HD;        // heads
   constexpr int HL = H / 2;         // heads per softmax warpgroup (head h belongs to warpgroup h & 1)
@@ -122,6 +124,12 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
     prefetch_tensormap(&mapK);
     prefetch_tensormap(&mapV);
   }
+  if (GROUPS == 2) {
+    // the pad half of every head slot and the rows >= F are written here once and never again
+    uint4* z = reinterpret_cast<uint4*>(sm.q[0]);
+    for (int i = threadIdx.x; i < (2 + 2 * kStages) * kTileBytes / 16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -133,13 +141,13 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
     // ------------------------------------------------------------------ producer / scheduler
     // The whole warp walks the node list (dynamic scheduler); lane 0 drives the mbarriers and TMA.
     // Isolated nodes never enter the pipeline: the warp writes their zero rows directly.
+    if constexpr (GROUPS == 1) {
     uint32_t qi = 0, ei = 0;
     for (;;) {
-      int node = -1, pb = 0, pe = 0, grp = 0;
+      int node = -1, pb = 0, pe = 0;
+      const int grp = 0;
       if (lane == 0) {
-        const int idx = atomicAdd(counter, 1);
-        const int ni = GROUPS == 1 ? idx : idx / GROUPS;
-        grp = GROUPS == 1 ? 0 : idx - ni * GROUPS;
+        const int ni = atomicAdd(counter, 1);
         node = ni < N ? (order ? order[ni] : ni) : -1;
         if (node >= 0) {
           pb = rowptr[node];
@@ -149,9 +157,8 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       node = __shfl_sync(0xffffffffu, node, 0);
       pb = __shfl_sync(0xffffffffu, pb, 0);
       pe = __shfl_sync(0xffffffffu, pe, 0);
-      grp = __shfl_sync(0xffffffffu, grp, 0);
       if (node >= 0 && pe == pb) {
-        if (accumulate || grp != 0) continue;   // later ring phase: rows hold the earlier sum; group 0 zero-fills the whole row
+        if (accumulate) continue;   // a later ring phase: the node's rows already hold the earlier phases' sum
         float4* z = reinterpret_cast<float4*>(agg + (int64_t)node * F * kD);
         for (int i = lane; i < F * (kD / 4); i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         continue;
@@ -173,8 +180,7 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
             mbar_arrive(&sm.q_full[qb]);
           } else {
             mbar_arrive_expect_tx(&sm.q_full[qb], kTileBytes);
-            if (GROUPS == 1) tma_load_3d(sm.q[qb], &mapQ, &sm.q_full[qb], 0, 0, node);
-            else tma_load_4d(sm.q[qb], &mapQ, &sm.q_full[qb], 0, 4 * grp, 0, node);
+            tma_load_3d(sm.q[qb], &mapQ, &sm.q_full[qb], 0, 0, node);
             int src_next = dst_src[pb];
             for (int p = pb; p < pe; ++p, ++ei) {
               const int src = src_next;
@@ -185,13 +191,8 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
                 break;
               }
               mbar_arrive_expect_tx(&sm.kv_full[st], 2 * kTileBytes);
-              if (GROUPS == 1) {
-                tma_load_3d(sm.kv[st][0], &mapK, &sm.kv_full[st], 0, 0, src);
-                tma_load_3d(sm.kv[st][1], &mapV, &sm.kv_full[st], 0, 0, src);
-              } else {
-                tma_load_4d(sm.kv[st][0], &mapK, &sm.kv_full[st], 0, 4 * grp, 0, src);
-                tma_load_4d(sm.kv[st][1], &mapV, &sm.kv_full[st], 0, 4 * grp, 0, src);
-              }
+              tma_load_3d(sm.kv[st][0], &mapK, &sm.kv_full[st], 0, 0, src);
+              tma_load_3d(sm.kv[st][1], &mapV, &sm.kv_full[st], 0, 0, src);
             }
           }
           ++qi;
@@ -200,6 +201,79 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       failed = __shfl_sync(0xffffffffu, failed, 0);
       if (failed) AMP_FAIL(failed);
       if (node < 0) break;
+    }
+    } else {
+    // head_dim 8: the whole warp copies (cp.async); a load unit (the Q tile of a work item, or an edge's K and V tiles) is one
+    // commit group, and the full barrier of unit u is raised when unit u + 1 has been issued (wait_group 1, proxy fence,
+    // arrive): every wait of this warp only depends on units older than the newest one, so nothing can deadlock.
+    uint32_t qi = 0, ei = 0, pend = 0;
+    auto retire = [&](uint32_t next_bar) {
+      cp_async_commit();
+      if (pend) {
+        cp_async_wait<1>();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_a(pend);
+      }
+      pend = next_bar;
+    };
+    for (;;) {
+      int node = -1, pb = 0, pe = 0, grp = 0;
+      if (lane == 0) {
+        const int idx = atomicAdd(counter, 1);
+        const int ni = idx / GROUPS;
+        grp = idx - ni * GROUPS;
+        node = ni < N ? (order ? order[ni] : ni) : -1;
+        if (node >= 0) {
+          pb = rowptr[node];
+          pe = rowptr[node + 1];
+        }
+      }
+      node = __shfl_sync(0xffffffffu, node, 0);
+      pb = __shfl_sync(0xffffffffu, pb, 0);
+      pe = __shfl_sync(0xffffffffu, pe, 0);
+      grp = __shfl_sync(0xffffffffu, grp, 0);
+      if (node >= 0 && pe == pb) {
+        if (accumulate || grp != 0) continue;   // later ring phase: rows hold the earlier sum; group 0 zero-fills the whole row
+        float4* z = reinterpret_cast<float4*>(agg + (int64_t)node * F * kD);
+        for (int i = lane; i < F * (kD / 4); i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        continue;
+      }
+      const uint32_t qb = qi & 1;
+      int failed = 0;
+      if (lane == 0) {
+        if (!mbar_wait(&sm.q_empty[qb], ((qi >> 1) & 1) ^ 1)) {
+          failed = 101;
+        } else {
+          NodeSlot ns;
+          ns.node = node;
+          ns.p_begin = pb;
+          ns.p_end = pe;
+          ns.inv_deg = node >= 0 ? inv_deg[node] : 0.f;
+          ns.grp = grp;
+          sm.slot[qb] = ns;
+          if (node < 0) mbar_arrive(&sm.q_full[qb]);
+        }
+      }
+      failed = __shfl_sync(0xffffffffu, failed, 0);
+      if (failed) AMP_FAIL(failed);
+      if (node < 0) break;
+      load_padded_tile(smem_u32(sm.q[qb]), gq, node, F, grp, lane);
+      retire(smem_u32(&sm.q_full[qb]));
+      for (int p = pb; p < pe; ++p, ++ei) {
+        const int src = dst_src[p];
+        const uint32_t st = ei % kStages;
+        if (lane == 0 && !mbar_wait(&sm.kv_empty[st], ((ei / kStages) & 1) ^ 1)) failed = 102;
+        failed = __shfl_sync(0xffffffffu, failed, 0);
+        if (failed) AMP_FAIL(failed);
+        load_padded_tile(smem_u32(sm.kv[st][0]), gk, src, F, grp, lane);
+        load_padded_tile(smem_u32(sm.kv[st][1]), gv, src, F, grp, lane);
+        retire(smem_u32(&sm.kv_full[st]));
+      }
+      ++qi;
+    }
+    retire(0u);        // raises the last unit's barrier (the empty group it commits completes at once)
+    cp_async_wait<0>();
     }
   } else if (warp == 9) {
     // ------------------------------------------------------------------ score MMAs (all heads)
@@ -420,6 +494,7 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
 #undef AMP_PHASE
   }
 fail:
+  if (GROUPS == 2) cp_async_wait<0>();   // no copy into this CTA's shared memory may outlive it
   tc_fence_before();
   __syncthreads();
   if (warp == 9) tmem_dealloc(tmem, 512);
@@ -452,13 +527,9 @@ static int attn_fwd_bf16_impl(const void* q, const void* k, const void* v,
   cudaStream_t stream = as_stream(stream_);
   CUtensorMap mq, mk, mv;
   const int hd = d / H;
-  if (hd == 8) {
-    if (!make_tensor_map_bf16_hd8(&mq, q, F, N) || !make_tensor_map_bf16_hd8(&mk, k, F, N_kv) || !make_tensor_map_bf16_hd8(&mv, v, F, N_kv))
-      return AMPCONV_ERR_CUDA;
-  } else if (!make_tensor_map_bf16_3d(&mq, q, kD, F, N, kD, 128) || !make_tensor_map_bf16_3d(&mk, k, kD, F, N_kv, kD, 128) ||
-             !make_tensor_map_bf16_3d(&mv, v, kD, F, N_kv, kD, 128)) {
-    return AMPCONV_ERR_CUDA;
-  }
+  if (!make_tensor_map_bf16_3d(&mq, q, kD, F, N, kD, 128) || !make_tensor_map_bf16_3d(&mk, k, kD, F, N_kv, kD, 128) ||
+      !make_tensor_map_bf16_3d(&mv, v, kD, F, N_kv, kD, 128))
+    return AMPCONV_ERR_CUDA;   // (head_dim 8 loads its tiles with cp.async from the raw pointers instead)
   int* counter = reinterpret_cast<int*>(workspace);
   int* status = counter + 1;
   AMPCONV_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(int), stream));   // the status word (counter + 1) is the caller's: zeroed once per layer call
@@ -470,7 +541,10 @@ static int attn_fwd_bf16_impl(const void* q, const void* k, const void* v,
     AMPCONV_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_bf16_kernel<HDV, GRP, PROFV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                           (int)smem));                                                                \
     attn_fwd_bf16_kernel<HDV, GRP, PROFV><<<grid, kFwdThreads, smem, stream>>>(mq, mk, mv, dst_rowptr, dst_src, inv_deg, order, \
-                                                                         counter, status, agg, lse2, (int)n_work, F, accumulate, prof);  \
+                                                                         counter, status, agg, lse2, (int)n_work, F, accumulate,         \
+                                                                         reinterpret_cast<const uint8_t*>(q),                \
+                                                                         reinterpret_cast<const uint8_t*>(k),                \
+                                                                         reinterpret_cast<const uint8_t*>(v), prof);         \
   } while (0)
   if (hd == 8) {
     AMP_LAUNCH_FWD(16, 2, false);

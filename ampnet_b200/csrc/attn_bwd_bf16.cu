@@ -53,7 +53,13 @@ constexpr int kStatFloats = 4 * 128;   // H * roundup4(F) <= 512 floats per edge
 // Share of the exponentials evaluated on the FMA pipe (umma.cuh: ex2_poly2) instead of MUFU: every fourth pair of score
 // columns when enabled.  The forward gained 4 % from it; in these passes it is NOT measured yet, so the
 // switches stay off and the compiled kernels are unchanged.
-constexpr bool kPolyShareDq = false, kPolyShareDkv = false;
+#ifndef AMP_POLY_DQ
+#define AMP_POLY_DQ 0
+#endif
+#ifndef AMP_POLY_DKV
+#define AMP_POLY_DKV 0
+#endif
+constexpr bool kPolyShareDq = AMP_POLY_DQ != 0, kPolyShareDkv = AMP_POLY_DKV != 0;
 
 struct NodeSlot {
   int node, e_begin, e_end;
@@ -143,7 +149,9 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
                      const int32_t* __restrict__ slot_of, const int32_t* __restrict__ order,
                      const float* __restrict__ lse2, float* __restrict__ delta, float* __restrict__ d_qkv, int* __restrict__ counter, int* __restrict__ status,
                      int N, int F, float out_scale0, float out_scale1, int out_ld, int out_c0, int out_c1,
-                     uint16_t* __restrict__ halo_bf16, int halo_from, int accumulate, long long* __restrict__ prof) {
+                     uint16_t* __restrict__ halo_bf16, int halo_from, int accumulate,
+                     const uint8_t* __restrict__ gown0, const uint8_t* __restrict__ gown1,
+                     const uint8_t* __restrict__ goth0, const uint8_t* __restrict__ goth1, long long* __restrict__ prof) {
   using Smem = BwdSmem<MODE>;
   constexpr int NS = Smem::NS;
   constexpr int H = kD / HD;          // heads of a work item
@@ -169,7 +177,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       mbar_init(&sm.op_full[i], kEwWarps / 2);
     }
     for (int i = 0; i < NS; ++i) {
-      mbar_init(&sm.edge_full[i], 1);
+      mbar_init(&sm.edge_full[i], GROUPS == 2 ? 2 : 1);   // head_dim 8: bulk copies of the statistics + the cp.async unit
       mbar_init(&sm.edge_empty[i], 3 + (MODE == MODE_DQ ? kEwWarps : kFoldWarps));   // the readers of the statistics rows
     }
     for (int i = 0; i < 32; ++i) mbar_init(&sm.dl_bar[i >> 2][i & 3], 4);
@@ -195,6 +203,12 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
     }
     fence_proxy_async_smem();
   }
+  if (GROUPS == 2) {
+    // the pad half of every head slot and the rows >= F are written here once and never again
+    uint4* z = reinterpret_cast<uint4*>(sm.own[0][0]);
+    for (int i = threadIdx.x; i < (4 + 2 * NS) * kTileBytes / 16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+  }
   if (warp == kEwWarps && lane == 0) {
     prefetch_tensormap(&own0);
     prefetch_tensormap(&own1);
@@ -213,13 +227,13 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
     // ------------------------------------------------------------------ producer / scheduler
     if (MODE == MODE_DQ) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     else asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    if constexpr (GROUPS == 1) {
     uint32_t qi = 0, ei = 0;
     for (;;) {
-      int node = -1, eb = 0, ee = 0, grp = 0;
+      int node = -1, eb = 0, ee = 0;
+      const int grp = 0;
       if (lane == 0) {
-        const int idx = atomicAdd(counter, 1);
-        const int ni = GROUPS == 1 ? idx : idx / GROUPS;
-        grp = GROUPS == 1 ? 0 : idx - ni * GROUPS;
+        const int ni = atomicAdd(counter, 1);
         node = ni < N ? (order ? order[ni] : ni) : -1;
         if (node >= 0) {
           eb = rowptr[node];
@@ -229,11 +243,10 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       node = __shfl_sync(0xffffffffu, node, 0);
       eb = __shfl_sync(0xffffffffu, eb, 0);
       ee = __shfl_sync(0xffffffffu, ee, 0);
-      grp = __shfl_sync(0xffffffffu, grp, 0);
       if (node >= 0 && ee == eb) {
         // node without edges in this pass: its gradient rows are zero (halo sources always have an edge)
         if (halo_bf16 != nullptr && node >= halo_from) continue;
-        if (accumulate || grp != 0) continue;   // later ring phase: rows hold the earlier sum; group 0 zero-fills whole rows
+        if (accumulate) continue;   // a later ring phase: the node's rows already hold the earlier phases' sum
         const int nblk = MODE == MODE_DQ ? 1 : 2;
         for (int i = lane; i < F * nblk * (kD / 4); i += 32) {
           const int r = i / (nblk * (kD / 4)), rem = i - r * (nblk * (kD / 4));
@@ -259,13 +272,8 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
             mbar_arrive(&sm.own_full[qb]);
           } else {
             mbar_arrive_expect_tx(&sm.own_full[qb], 2 * kTileBytes);
-            if (GROUPS == 1) {
-              tma_load_3d(sm.own[qb][0], &own0, &sm.own_full[qb], 0, 0, node);
-              tma_load_3d(sm.own[qb][1], &own1, &sm.own_full[qb], 0, 0, node);
-            } else {
-              tma_load_4d(sm.own[qb][0], &own0, &sm.own_full[qb], 0, 4 * grp, 0, node);
-              tma_load_4d(sm.own[qb][1], &own1, &sm.own_full[qb], 0, 4 * grp, 0, node);
-            }
+            tma_load_3d(sm.own[qb][0], &own0, &sm.own_full[qb], 0, 0, node);
+            tma_load_3d(sm.own[qb][1], &own1, &sm.own_full[qb], 0, 0, node);
             int nb_next = nbr[eb];
             for (int e = eb; e < ee; ++e, ++ei) {
               const int nb = nb_next;
@@ -284,13 +292,8 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
                 mbar_arrive_expect_tx(&sm.edge_full[st], 2 * kTileBytes + stat_bytes);
                 bulk_load(sm.stat[st][0], lse2 + ((int64_t)e * HT + grp * H) * Fs, stat_bytes, &sm.edge_full[st]);
               }
-              if (GROUPS == 1) {
-                tma_load_3d(sm.edge[st][0], &oth0, &sm.edge_full[st], 0, 0, nb);
-                tma_load_3d(sm.edge[st][1], &oth1, &sm.edge_full[st], 0, 0, nb);
-              } else {
-                tma_load_4d(sm.edge[st][0], &oth0, &sm.edge_full[st], 0, 4 * grp, 0, nb);
-                tma_load_4d(sm.edge[st][1], &oth1, &sm.edge_full[st], 0, 4 * grp, 0, nb);
-              }
+              tma_load_3d(sm.edge[st][0], &oth0, &sm.edge_full[st], 0, 0, nb);
+              tma_load_3d(sm.edge[st][1], &oth1, &sm.edge_full[st], 0, 0, nb);
             }
           }
           ++qi;
@@ -299,6 +302,98 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
       failed = __shfl_sync(0xffffffffu, failed, 0);
       if (failed) AMP_FAIL(failed);
       if (node < 0) break;
+    }
+    } else {
+    // head_dim 8: tiles are built by the whole warp with cp.async (umma.cuh: load_padded_tile); a load unit (a work item's own
+    // tiles, or an edge's tiles) is one commit group whose full barrier is raised once the NEXT unit has been issued
+    // (wait_group 1, proxy fence, arrive).  The statistics rows still travel as bulk copies on the same barrier, which
+    // therefore counts two arrivals per phase.
+    uint32_t qi = 0, ei = 0, pend = 0;
+    auto retire = [&](uint32_t next_bar) {
+      cp_async_commit();
+      if (pend) {
+        cp_async_wait<1>();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_a(pend);
+      }
+      pend = next_bar;
+    };
+    for (;;) {
+      int node = -1, eb = 0, ee = 0, grp = 0;
+      if (lane == 0) {
+        const int idx = atomicAdd(counter, 1);
+        const int ni = idx / GROUPS;
+        grp = idx - ni * GROUPS;
+        node = ni < N ? (order ? order[ni] : ni) : -1;
+        if (node >= 0) {
+          eb = rowptr[node];
+          ee = rowptr[node + 1];
+        }
+      }
+      node = __shfl_sync(0xffffffffu, node, 0);
+      eb = __shfl_sync(0xffffffffu, eb, 0);
+      ee = __shfl_sync(0xffffffffu, ee, 0);
+      grp = __shfl_sync(0xffffffffu, grp, 0);
+      if (node >= 0 && ee == eb) {
+        if (halo_bf16 != nullptr && node >= halo_from) continue;
+        if (accumulate || grp != 0) continue;   // later ring phase: rows hold the earlier sum; group 0 zero-fills whole rows
+        const int nblk = MODE == MODE_DQ ? 1 : 2;
+        for (int i = lane; i < F * nblk * (kD / 4); i += 32) {
+          const int r = i / (nblk * (kD / 4)), rem = i - r * (nblk * (kD / 4));
+          const int blk = rem / (kD / 4), c4 = rem - blk * (kD / 4);
+          *reinterpret_cast<float4*>(d_qkv + ((int64_t)node * F + r) * out_ld + (blk == 0 ? out_c0 : out_c1) + 4 * c4) =
+              make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        continue;
+      }
+      const uint32_t qb = qi & 1;
+      int failed = 0;
+      if (lane == 0) {
+        if (!mbar_wait(&sm.own_empty[qb], ((qi >> 1) & 1) ^ 1)) {
+          failed = 101;
+        } else {
+          NodeSlot ns;
+          ns.node = node;
+          ns.e_begin = eb;
+          ns.e_end = ee;
+          ns.grp = grp;
+          sm.slot[qb] = ns;
+          if (node < 0) mbar_arrive(&sm.own_full[qb]);
+        }
+      }
+      failed = __shfl_sync(0xffffffffu, failed, 0);
+      if (failed) AMP_FAIL(failed);
+      if (node < 0) break;
+      load_padded_tile(smem_u32(sm.own[qb][0]), gown0, node, F, grp, lane);
+      load_padded_tile(smem_u32(sm.own[qb][1]), gown1, node, F, grp, lane);
+      retire(smem_u32(&sm.own_full[qb]));
+      for (int e = eb; e < ee; ++e, ++ei) {
+        const int nb = nbr[e];
+        const uint32_t st = ei % NS;
+        if (lane == 0) {
+          if (!mbar_wait(&sm.edge_empty[st], ((ei / NS) & 1) ^ 1)) {
+            failed = 102;
+          } else if (MODE == MODE_DKV) {
+            const int64_t sl = slot_of ? slot_of[e] : e;
+            mbar_arrive_expect_tx(&sm.edge_full[st], 2 * stat_bytes);
+            bulk_load(sm.stat[st][0], lse2 + (sl * HT + grp * H) * Fs, stat_bytes, &sm.edge_full[st]);
+            bulk_load(sm.stat[st][1], delta + (sl * HT + grp * H) * Fs, stat_bytes, &sm.edge_full[st]);
+          } else {
+            mbar_arrive_expect_tx(&sm.edge_full[st], stat_bytes);
+            bulk_load(sm.stat[st][0], lse2 + ((int64_t)e * HT + grp * H) * Fs, stat_bytes, &sm.edge_full[st]);
+          }
+        }
+        failed = __shfl_sync(0xffffffffu, failed, 0);
+        if (failed) AMP_FAIL(failed);
+        load_padded_tile(smem_u32(sm.edge[st][0]), goth0, nb, F, grp, lane);
+        load_padded_tile(smem_u32(sm.edge[st][1]), goth1, nb, F, grp, lane);
+        retire(smem_u32(&sm.edge_full[st]));
+      }
+      ++qi;
+    }
+    retire(0u);
+    cp_async_wait<0>();
     }
   } else if (warp == W_SCORE) {
     // ------------------------------------------------------------------ score MMAs X, Y of every half-item
@@ -754,6 +849,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
 #undef AMP_TWAIT
   }
 fail:
+  if (GROUPS == 2) cp_async_wait<0>();   // no copy into this CTA's shared memory may outlive it
   tc_fence_before();
   __syncthreads();
   if (warp == W_SCORE) tmem_dealloc(tmem, 512);
@@ -763,6 +859,7 @@ long long* g_bwd_prof = nullptr;   // debug: set through ampconv_debug_set_bwd_p
 
 template <int HD, int MODE, int GROUPS>
 int launch_bwd(const CUtensorMap& own0, const CUtensorMap& own1, const CUtensorMap& oth0, const CUtensorMap& oth1,
+               const void* gown0, const void* gown1, const void* goth0, const void* goth1,
                const int32_t* rowptr, const int32_t* nbr, const int32_t* slot_of, const int32_t* order, const float* lse2,
                float* delta, float* d_qkv, int* counter, int* status, int N, int F, float s0, float s1, int out_ld, int out_c0,
                int out_c1, uint16_t* halo_bf16, int halo_from, int accumulate, cudaStream_t stream) {
@@ -776,7 +873,9 @@ int launch_bwd(const CUtensorMap& own0, const CUtensorMap& own1, const CUtensorM
                                           (int)smem));                                                                           \
     attn_bwd_bf16_kernel<HD, MODE, NH_, GROUPS, PROF_><<<grid, threads_of(MODE), smem, stream>>>(                                         \
         own0, own1, oth0, oth1, rowptr, nbr, slot_of, order, lse2, delta, d_qkv, counter, status, N, F, s0, s1, out_ld, out_c0,   \
-        out_c1, halo_bf16, halo_from, accumulate, prof_);                                                                                  \
+        out_c1, halo_bf16, halo_from, accumulate, reinterpret_cast<const uint8_t*>(gown0),                                      \
+        reinterpret_cast<const uint8_t*>(gown1), reinterpret_cast<const uint8_t*>(goth0),                                       \
+        reinterpret_cast<const uint8_t*>(goth1), prof_);                                                                                  \
   } while (0)
   if (prof && GROUPS == 1) {
     if (F > 64) AMP_LAUNCH_BWD(2, true, prof);
@@ -816,14 +915,9 @@ static int bwd_common(int mode, const void* q, const void* k, const void* v, con
   cudaStream_t stream = as_stream(stream_);
   CUtensorMap mq, mk, mv, mg;
   const int64_t nd = N_dst > 0 ? N_dst : 1, nk = N_kv > 0 ? N_kv : 1;
-  if (d / H == 8) {
-    if (!make_tensor_map_bf16_hd8(&mq, q, F, nd) || !make_tensor_map_bf16_hd8(&mk, k, F, nk) ||
-        !make_tensor_map_bf16_hd8(&mv, v, F, nk) || !make_tensor_map_bf16_hd8(&mg, d_agg_bf16, F, nd))
-      return AMPCONV_ERR_CUDA;
-  } else if (!make_tensor_map_bf16_3d(&mq, q, kD, F, nd, kD, 128) || !make_tensor_map_bf16_3d(&mk, k, kD, F, nk, kD, 128) ||
-             !make_tensor_map_bf16_3d(&mv, v, kD, F, nk, kD, 128) || !make_tensor_map_bf16_3d(&mg, d_agg_bf16, kD, F, nd, kD, 128)) {
-    return AMPCONV_ERR_CUDA;
-  }
+  if (!make_tensor_map_bf16_3d(&mq, q, kD, F, nd, kD, 128) || !make_tensor_map_bf16_3d(&mk, k, kD, F, nk, kD, 128) ||
+      !make_tensor_map_bf16_3d(&mv, v, kD, F, nk, kD, 128) || !make_tensor_map_bf16_3d(&mg, d_agg_bf16, kD, F, nd, kD, 128))
+    return AMPCONV_ERR_CUDA;   // (head_dim 8 loads its tiles with cp.async from the raw pointers instead)
   int* counter = reinterpret_cast<int*>(workspace) + (mode == MODE_DQ ? 2 : 4);
   int* status = reinterpret_cast<int*>(workspace) + 1;
   AMPCONV_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(int), stream));
@@ -833,22 +927,22 @@ static int bwd_common(int mode, const void* q, const void* k, const void* v, con
   if (mode == MODE_DQ) {
     // dQ = hd^-1/2 * (dS K)
     if (hd == 8)
-      return launch_bwd<16, MODE_DQ, 2>(mq, mg, mk, mv, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)n_work, F,
+      return launch_bwd<16, MODE_DQ, 2>(mq, mg, mk, mv, q, d_agg_bf16, k, v, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)n_work, F,
                                        inv_sqrt_hd, 0.f, out_ld, out_c0, out_c1, nullptr, 0, accumulate, stream);
     if (hd == 16)
-      return launch_bwd<16, MODE_DQ, 1>(mq, mg, mk, mv, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)n_work, F,
+      return launch_bwd<16, MODE_DQ, 1>(mq, mg, mk, mv, q, d_agg_bf16, k, v, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)n_work, F,
                                     inv_sqrt_hd, 0.f, out_ld, out_c0, out_c1, nullptr, 0, accumulate, stream);
-    return launch_bwd<32, MODE_DQ, 1>(mq, mg, mk, mv, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)n_work, F,
+    return launch_bwd<32, MODE_DQ, 1>(mq, mg, mk, mv, q, d_agg_bf16, k, v, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)n_work, F,
                                   inv_sqrt_hd, 0.f, out_ld, out_c0, out_c1, nullptr, 0, accumulate, stream);
   }
   // dK = hd^-1/2 * dS^T Q = ln2 * dS^T Q'  (Q' = Q * log2e / sqrt(hd)),  dV = P^T dO
   if (hd == 8)
-    return launch_bwd<16, MODE_DKV, 2>(mk, mv, mq, mg, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)n_work, F,
+    return launch_bwd<16, MODE_DKV, 2>(mk, mv, mq, mg, k, v, q, d_agg_bf16, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)n_work, F,
                                       ln2, 1.f, out_ld, out_c0, out_c1, reinterpret_cast<uint16_t*>(halo_bf16), (int)halo_from, 0, stream);
   if (hd == 16)
-    return launch_bwd<16, MODE_DKV, 1>(mk, mv, mq, mg, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)n_work, F,
+    return launch_bwd<16, MODE_DKV, 1>(mk, mv, mq, mg, k, v, q, d_agg_bf16, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)n_work, F,
                                    ln2, 1.f, out_ld, out_c0, out_c1, reinterpret_cast<uint16_t*>(halo_bf16), (int)halo_from, 0, stream);
-  return launch_bwd<32, MODE_DKV, 1>(mk, mv, mq, mg, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)n_work, F, ln2,
+  return launch_bwd<32, MODE_DKV, 1>(mk, mv, mq, mg, k, v, q, d_agg_bf16, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)n_work, F, ln2,
                                  1.f, out_ld, out_c0, out_c1, reinterpret_cast<uint16_t*>(halo_bf16), (int)halo_from, 0, stream);
 }
 
@@ -909,29 +1003,38 @@ extern "C" int ampconv_attn_bwd_dkv_bf16_halo(const void* q, const void* k, cons
 //               (and zero-fills destinations without an edge), accumulate = 1 adds this phase's contribution; delta is
 //               indexed by the PHASE's destination-sorted slots and consumed by the same phase's _dkv launch.
 //   _dkv_phase: the `n_work` sources listed in `order`, all inside the phase's compact-id range.  Own sources
-//               (halo_from >= num_kv_nodes, d_kv_halo NULL) go to d_kv_own fp32 [num_own*F, 128]; the halo sources of the
+//               (d_kv_halo NULL) go to d_kv_own fp32: row r at d_kv_own[r * own_ld], dK at column own_dk_col, dV at
+//               own_dv_col (a dense [rows, 128] tensor or the dK | dV columns of d_qkv [rows, 192]); the halo sources of the
 //               phase's owner, compact ids [halo_from, ...), go as bf16 rows to d_kv_halo[(id - halo_from)*F, 128]: the
 //               block that travels to that owner.
 extern "C" int ampconv_attn_bwd_dq_bf16_phase(const void* q, const void* k, const void* v, const void* d_agg_bf16,
                                               const float* lse2, const int32_t* dst_rowptr, const int32_t* dst_src,
-                                              const int32_t* order, int64_t n_work, int accumulate, float* d_q, float* delta,
+                                              const int32_t* order, int64_t n_work, int accumulate, float* d_q, int64_t d_q_ld,
+                                              float* delta,
                                               int64_t num_nodes, int64_t num_kv_nodes, int64_t E, int F, int d, int H,
                                               void* workspace, size_t workspace_bytes, void* stream) {
-  AMPCONV_REQUIRE(n_work >= 0 && order != nullptr);
-  return bwd_common(MODE_DQ, q, k, v, d_agg_bf16, dst_rowptr, dst_src, nullptr, order, lse2, delta, d_q, kD, 0, 0, num_nodes,
+  AMPCONV_REQUIRE(n_work >= 0 && order != nullptr && d_q_ld >= kD && d_q_ld % 4 == 0);
+  return bwd_common(MODE_DQ, q, k, v, d_agg_bf16, dst_rowptr, dst_src, nullptr, order, lse2, delta, d_q, (int)d_q_ld, 0, 0, num_nodes,
                     num_kv_nodes, E, F, d, H, workspace, workspace_bytes, stream, nullptr, 0, n_work, accumulate);
 }
 
 extern "C" int ampconv_attn_bwd_dkv_bf16_phase(const void* q, const void* k, const void* v, const void* d_agg_bf16,
                                                const float* lse2, const float* delta, const int32_t* src_rowptr,
                                                const int32_t* src_dst, const int32_t* src_pos, const int32_t* order,
-                                               int64_t n_work, float* d_kv_own, void* d_kv_halo, int64_t halo_from,
+                                               int64_t n_work, float* d_kv_own, int64_t own_ld, int64_t own_dk_col,
+                                               int64_t own_dv_col, void* d_kv_halo, int64_t halo_from,
                                                int64_t num_nodes, int64_t num_kv_nodes, int64_t E, int F, int d, int H,
                                                void* workspace, size_t workspace_bytes, void* stream) {
-  AMPCONV_REQUIRE(n_work >= 0 && order != nullptr && halo_from >= 0 && (d_kv_own != nullptr || d_kv_halo != nullptr));
+  AMPCONV_REQUIRE(n_work >= 0 && order != nullptr && halo_from >= 0 && ((d_kv_own != nullptr) != (d_kv_halo != nullptr)));
+  if (d_kv_halo != nullptr)      // a halo phase: only the owner's bf16 block [*, 128] = dK | dV is written
+    return bwd_common(MODE_DKV, q, k, v, d_agg_bf16, src_rowptr, src_dst, src_pos, order, lse2, const_cast<float*>(delta), nullptr,
+                      2 * kD, 0, kD, num_nodes, num_kv_nodes, E, F, d, H, workspace, workspace_bytes, stream, d_kv_halo,
+                      halo_from, n_work, 0);
+  AMPCONV_REQUIRE(own_ld >= 2 * kD && own_ld % 4 == 0 && own_dk_col % 4 == 0 && own_dv_col % 4 == 0 && own_dk_col + kD <= own_ld &&
+                  own_dv_col + kD <= own_ld);
   return bwd_common(MODE_DKV, q, k, v, d_agg_bf16, src_rowptr, src_dst, src_pos, order, lse2, const_cast<float*>(delta), d_kv_own,
-                    2 * kD, 0, kD, num_nodes, num_kv_nodes, E, F, d, H, workspace, workspace_bytes, stream, d_kv_halo,
-                    d_kv_halo ? halo_from : num_kv_nodes, n_work, 0);
+                    (int)own_ld, (int)own_dk_col, (int)own_dv_col, num_nodes, num_kv_nodes, E, F, d, H, workspace, workspace_bytes,
+                    stream, nullptr, num_kv_nodes, n_work, 0);
 }
 
 // Debug: when set to a device buffer of 64 int64, the next backward launches run the instrumented kernel and fill it

@@ -148,11 +148,31 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
+// ------------------------------------------------------------------------------------------
+// head_dim 8 (embed 64, 8 heads) on the head_dim-16 pipeline: a work item is (node, head group g of four heads) and its tiles
+// are the node's rows with every head zero-padded from 8 to 16 columns -- built ON THE WAY INTO SHARED MEMORY, nothing padded
+// exists in HBM.  A warp copies the 16 real bytes of every (token row, head) with cp.async (LDGSTS.128) into chunk 2 hh of the
+// 128B-swizzled row; the odd chunks and the rows >= F are zeroed once per kernel and never written again.  (A 4-D / 5-D TMA
+// box with a 16- or 32-byte inner extent under SWIZZLE_128B faults on this driver -- tools/tma_pad_probe.cu, profiles/.)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async_16(uint32_t smem_addr, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// tile <- rows [0, F) of node `node` of the bf16 tensor `base` [*, F, 64], heads 4 grp .. 4 grp + 3 (called by a full warp)
+__device__ __forceinline__ void load_padded_tile(uint32_t tile_smem, const uint8_t* __restrict__ base, int64_t node, int F,
+                                                 int grp, int lane) {
+  const uint8_t* src = base + node * F * 128 + grp * 64;
+  const int chunks = F * 4;
+#pragma unroll 4
+  for (int i = lane; i < chunks; i += 32) {
+    const int r = i >> 2, hh = i & 3;
+    cp_async_16(tile_smem + (uint32_t)(r * 128 + (((2 * hh) ^ (r & 7)) << 4)), src + r * 128 + hh * 16);
+  }
 }
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
   asm volatile(
@@ -415,24 +435,6 @@ inline bool make_tensor_map_bf16_3d(CUtensorMap* map, const void* base, uint64_t
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
-}
-
-// head_dim 8 (embed 64, 8 heads) as padded head_dim-16 tiles WITHOUT padded copies in HBM: the bf16 tensor [N][F][64] is
-// described as 4-D {8 columns of a head, 8 heads, F tokens, N nodes}; a box {16, 4, 128, 1} at head coordinate 4g asks for 16
-// columns per head, of which only 8 exist -- TMA zero-fills the out-of-bounds half.  The shared-memory tile is then the 128 x
-// (4 heads x (8 real + 8 zero columns)) K-major tile the head_dim-16 kernels consume (dense in traversal order: 128 bytes per
-// token row, 128B swizzle on the linear address); only the real bytes travel.
-inline bool make_tensor_map_bf16_hd8(CUtensorMap* map, const void* base, uint64_t F, uint64_t N) {
-  PFN_tensorMapEncodeTiled enc = tensor_map_encoder();
-  if (!enc) return false;
-  cuuint64_t dims[4] = {8, 8, F, N};
-  cuuint64_t strides[3] = {16, 128, F * 128};
-  cuuint32_t box[4] = {16, 4, 128, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }

@@ -446,7 +446,7 @@ class _DistAMPConvFunction(torch.autograd.Function):
         return d_x, outs[0], outs[1], outs[2], outs[3], None, None, None
 
 
-def forward_phases(q, k_all, v_all, pgs, num_kv_nodes, f, d, h, ws, stream, agg, before_phase=None):
+def forward_phases(q, k_all, v_all, pgs, num_kv_nodes, f, d, h, ws, stream, agg, before_phase=None, after_phase=None):
     """The ring phases of the forward attention on `stream`: phase 0 (own sources) overwrites agg, phases 1.. add to it;
     before_phase(t) is called right before phase t >= 1 is launched (the peer path waits there for the phase's K|V rows).
     Returns the per-phase lse2 tensors."""
@@ -465,39 +465,43 @@ def forward_phases(q, k_all, v_all, pgs, num_kv_nodes, f, d, h, ws, stream, agg,
                   pgs.order_dst[t], _lib.i64(n_work), _lib.i32(0 if t == 0 else 1), agg, l2,
                   _lib.i64(n), _lib.i64(num_kv_nodes), _lib.i64(g.num_edges), _lib.i32(f), _lib.i32(d),
                   _lib.i32(h), ws, _lib.size_t(256), st)
+        if after_phase is not None:
+            after_phase(t)
     return lse2
 
 
-def backward_phases(q, k_all, v_all, d_agg, lse2, pgs, plan, num_kv_nodes, f, d, h, ws, stream, d_q, d_kv, send_slot,
+def backward_phases(q, k_all, v_all, d_agg, lse2, pgs, plan, num_kv_nodes, f, d, h, ws, stream, d_qkv, send_slot,
                     after_halo_phase):
-    """The ring phases of the attention backward on `stream`: per phase dQ (first executed phase overwrites d_q, the others
-    add) then dK|dV of the phase's sources; halo phases first -- send_slot(t) -> (slot, bf16 buffer) receives the phase
-    owner's block and after_halo_phase(t, slot) ships it -- own sources last, into d_kv fp32."""
-    n = d_q.shape[0] // f
+    """The ring phases of the attention backward on `stream`: per phase dQ (first executed phase overwrites, the others add)
+    then dK|dV of the phase's sources; halo phases first -- send_slot(t) -> (slot, bf16 buffer) receives the phase owner's
+    block and after_halo_phase(t, slot) ships it -- own sources last.  d_qkv fp32 [rows, 3d] = dQ | dK | dV of the own rows."""
+    n = d_qkv.shape[0] // f
     fs = (f + 3) // 4 * 4
     st = _lib.stream_ptr(stream)
     world = len(pgs.graphs)
-    delta = torch.empty((max(pgs.max_phase_edges, 1), h, fs), dtype=torch.float32, device=d_q.device)
+    delta = torch.empty((max(pgs.max_phase_edges, 1), h, fs), dtype=torch.float32, device=d_qkv.device)
     first = True
     for t in list(range(1, world)) + [0]:
         g = pgs.graphs[t]
         n_work = n if first else pgs.n_dst_active[t]
         _lib.call("ampconv_attn_bwd_dq_bf16_phase", q, k_all, v_all, d_agg, lse2[t], g.dst_rowptr, g.dst_src,
-                  pgs.order_dst[t], _lib.i64(n_work), _lib.i32(0 if first else 1), d_q, delta,
+                  pgs.order_dst[t], _lib.i64(n_work), _lib.i32(0 if first else 1), d_qkv, _lib.i64(3 * d), delta,
                   _lib.i64(n), _lib.i64(num_kv_nodes), _lib.i64(g.num_edges), _lib.i32(f), _lib.i32(d), _lib.i32(h),
                   ws, _lib.size_t(256), st)
         first = False
         lo, hi = plan.src_range[t]
         if t == 0:
             _lib.call("ampconv_attn_bwd_dkv_bf16_phase", q, k_all, v_all, d_agg, lse2[t], delta, g.src_rowptr,
-                      g.src_dst, g.src_pos, pgs.order_src[t], _lib.i64(hi - lo), d_kv, None, _lib.i64(num_kv_nodes),
+                      g.src_dst, g.src_pos, pgs.order_src[t], _lib.i64(hi - lo), d_qkv, _lib.i64(3 * d), _lib.i64(d),
+                      _lib.i64(2 * d), None, _lib.i64(num_kv_nodes),
                       _lib.i64(n), _lib.i64(num_kv_nodes), _lib.i64(g.num_edges), _lib.i32(f), _lib.i32(d), _lib.i32(h),
                       ws, _lib.size_t(256), st)
             continue
         slot, buf = send_slot(t)
         if hi > lo:
             _lib.call("ampconv_attn_bwd_dkv_bf16_phase", q, k_all, v_all, d_agg, lse2[t], delta, g.src_rowptr,
-                      g.src_dst, g.src_pos, pgs.order_src[t], _lib.i64(hi - lo), None, buf, _lib.i64(lo),
+                      g.src_dst, g.src_pos, pgs.order_src[t], _lib.i64(hi - lo), None, _lib.i64(0), _lib.i64(0), _lib.i64(0),
+                      buf, _lib.i64(lo),
                       _lib.i64(n), _lib.i64(num_kv_nodes), _lib.i64(g.num_edges), _lib.i32(f), _lib.i32(d), _lib.i32(h),
                       ws, _lib.size_t(256), st)
         after_halo_phase(t, slot)      # an empty block still raises its flag
@@ -523,6 +527,8 @@ class PeerWindow:
             _lib.call("ampconv_peer_alloc", _lib.size_t(self.nbytes), ctypes.byref(ptr))
         self.ptr = int(ptr.value)
         self.t = torch.as_tensor(_RawCuda(self.ptr, self.nbytes), device=dev)
+        if self.t.data_ptr() != self.ptr or self.t.device != dev:
+            raise RuntimeError("torch copied the peer window instead of viewing it")
         handle = (ctypes.c_ubyte * 64)()
         with torch.cuda.device(dev):
             _lib.call("ampconv_peer_export", ctypes.c_void_p(self.ptr), handle)
@@ -587,6 +593,9 @@ class PeerEngine:
         kv_nodes = pg.num_kv_nodes
         a256 = lambda v: (v + 255) // 256 * 256
         self.k_off, self.v_off = 0, a256(kv_nodes * row_kv)
+        # every peer lays its window out from ITS OWN node count: V of rank p starts behind p's K rows
+        self.peer_v_off = [a256((int(pg.n_local_all[p_]) + sum(int(c) for c in pg.recv_matrix[p_])) * row_kv) for p_ in range(world)]
+        assert self.peer_v_off[pg.rank] == self.v_off
         self.kv_win = PeerWindow(self.v_off + a256(kv_nodes * row_kv), dev, group)
         self.k_all = self.kv_win.view(self.k_off, (kv_nodes * f, d), torch.bfloat16)
         self.v_all = self.kv_win.view(self.v_off, (kv_nodes * f, d), torch.bfloat16)
@@ -598,9 +607,14 @@ class PeerEngine:
         self.ramp = torch.empty(65536, dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             _lib.call("ampconv_peer_ramp", self.ramp, _lib.i32(65536), F_._stream(dev))
-        # forward staging: the rows every receiver needs, packed per receiver (send_idx order)
-        self.k_send = torch.empty((max(n_recv, 1), f * d), dtype=torch.bfloat16, device=dev)
-        self.v_send = torch.empty_like(self.k_send)
+        # forward staging: the K / V rows one receiver needs, packed (send_idx order); one slot per phase while it fits,
+        # else a ring of two (a slot is repacked once its push has left)
+        need_f = [2 * self.plan.fwd_rows[t] * row_kv for t in range(world)]
+        self.n_fslots = max(1, world - 1 if sum(need_f) <= SEND_SLOT_BUDGET_BYTES else 2)
+        frows = max([1] + self.plan.fwd_rows[1:])
+        self.k_send = [torch.empty((frows, f * d), dtype=torch.bfloat16, device=dev) for _ in range(self.n_fslots)]
+        self.v_send = [torch.empty((frows, f * d), dtype=torch.bfloat16, device=dev) for _ in range(self.n_fslots)]
+        self.fslot_free = [None] * self.n_fslots
         # backward staging: the bf16 dK|dV block of a phase's owner
         need = [self.plan.bwd_rows[t] * row_g for t in range(world)]
         self.n_slots = world - 1 if sum(need) <= SEND_SLOT_BUDGET_BYTES else 2
@@ -632,26 +646,32 @@ class PeerEngine:
         _lib.call("ampconv_peer_wait", ctypes.c_void_p(flag_ptr), _lib.i32(self.epoch), ws, ctypes.c_double(PEER_WAIT_SECONDS),
                   _lib.stream_ptr(stream))
 
-    def push_forward(self, compute):
-        """Packs the K / V rows every peer needs and pushes them around the ring on the copy stream."""
+    def push_forward(self, t, compute):
+        """Packs the K / V rows the receiver of ring phase t needs (compute stream) and pushes them into its K / V tensors
+        on the copy stream, then raises its forward flag."""
         pg, plan = self.pg, self.plan
-        n_send = int(sum(plan.send_counts))
+        p_ = plan.fwd_dst[t]
+        cnt = plan.fwd_rows[t]
+        slot = (t - 1) % self.n_fslots
         st = _lib.stream_ptr(compute)
-        if n_send:
+        if cnt:
+            if self.fslot_free[slot] is not None:
+                compute.wait_event(self.fslot_free[slot])
             rows = pg.n_local * self.f
-            _lib.call("ampconv_gather_rows", self.k_all[:rows], pg.send_idx, self.k_send, _lib.i64(n_send), _lib.i64(self.row_kv), st)
-            _lib.call("ampconv_gather_rows", self.v_all[:rows], pg.send_idx, self.v_send, _lib.i64(n_send), _lib.i64(self.row_kv), st)
+            idx = pg.send_idx[plan.send_off[p_]:plan.send_off[p_] + cnt]
+            _lib.call("ampconv_gather_rows", self.k_all[:rows], idx, self.k_send[slot], _lib.i64(cnt), _lib.i64(self.row_kv), st)
+            _lib.call("ampconv_gather_rows", self.v_all[:rows], idx, self.v_send[slot], _lib.i64(cnt), _lib.i64(self.row_kv), st)
         packed = torch.cuda.Event()
         packed.record(compute)
         self.comm.wait_event(packed)
-        for t in range(1, pg.world):
-            p_ = plan.fwd_dst[t]
-            nb = plan.fwd_rows[t] * self.row_kv
-            src_off = plan.send_off[p_] * self.row_kv
-            dst_off = plan.fwd_dst_off[t] * self.row_kv
-            self._copy(self.kv_win.peer[p_] + self.k_off + dst_off, self.k_send.data_ptr() + src_off, nb, self.comm)
-            self._copy(self.kv_win.peer[p_] + self.v_off + dst_off, self.v_send.data_ptr() + src_off, nb, self.comm)
-            self._signal(p_, 0, self.comm)
+        nb = cnt * self.row_kv
+        dst_off = plan.fwd_dst_off[t] * self.row_kv
+        self._copy(self.kv_win.peer[p_] + self.k_off + dst_off, self.k_send[slot].data_ptr(), nb, self.comm)
+        self._copy(self.kv_win.peer[p_] + self.peer_v_off[p_] + dst_off, self.v_send[slot].data_ptr(), nb, self.comm)
+        self._signal(p_, 0, self.comm)
+        ev = torch.cuda.Event()
+        ev.record(self.comm)
+        self.fslot_free[slot] = ev
 
     def push_backward(self, t, slot, compute):
         """Phase t's dK|dV block (in send slot `slot`) -> its owner's receive window."""
@@ -718,12 +738,19 @@ class _PeerAMPConvFunction(torch.autograd.Function):
             _lib.call("ampconv_qkv_proj_tc", x_local, w_in, b_in, q, eng.k_all, eng.v_all, _lib.i64(rows), _lib.i32(d),
                       _lib.f32(F_.LOG2E / hd ** 0.5), ws, st)
             TIMER.mark("fwd qkv projection")
-            eng.push_forward(compute)
+            for t in range(1, min(eng.n_fslots, world - 1) + 1):
+                eng.push_forward(t, compute)
             TIMER.mark("fwd pack K|V rows")
             agg = torch.empty((rows, d), dtype=torch.float32, device=dev)
             out = torch.empty((n, width), dtype=torch.float32, device=dev)
+
+            def after_phase(t):        # a staging slot is free again: pack and push the next receiver's rows
+                nxt = t + 1 + eng.n_fslots
+                if nxt < world:
+                    eng.push_forward(nxt, compute)
+
             lse2 = forward_phases(q, eng.k_all, eng.v_all, pgs, pg.num_kv_nodes, f, d, num_heads, ws, compute, agg,
-                                  before_phase=lambda t: eng.wait_flag(plan.ring[t], 0, ws, compute))
+                                  before_phase=lambda t: eng.wait_flag(plan.ring[t], 0, ws, compute), after_phase=after_phase)
             TIMER.mark("fwd attention (ring phases, K|V pushes overlapped)")
             _lib.call("ampconv_out_proj_tc", agg, w_out, b_out, pgs.has_in, out, _lib.i64(n), _lib.i32(f), _lib.i32(d), ws, st)
             TIMER.mark("fwd out projection")
@@ -761,8 +788,7 @@ class _PeerAMPConvFunction(torch.autograd.Function):
             _lib.call("ampconv_out_proj_bwd_params_tc", d_out, agg, pgs.has_in, d_w_out, d_b_out, _lib.i64(n), _lib.i32(f),
                       _lib.i32(d), ws, _lib.size_t(ws.numel()), bws, st)
             TIMER.mark("bwd out projection")
-            d_q = torch.empty((rows, d), dtype=torch.float32, device=dev)
-            d_kv = torch.empty((rows, 2 * d), dtype=torch.float32, device=dev)
+            d_qkv = torch.empty((rows, 3 * d), dtype=torch.float32, device=dev)
 
             def send_slot(t):
                 slot = (t - 1) % eng.n_slots
@@ -770,16 +796,15 @@ class _PeerAMPConvFunction(torch.autograd.Function):
                     compute.wait_event(eng.slot_free[slot])
                 return slot, eng.g_send[slot]
 
-            backward_phases(q, eng.k_all, eng.v_all, d_agg, lse2, pgs, plan, pg.num_kv_nodes, f, d, h, bws, compute, d_q, d_kv,
+            backward_phases(q, eng.k_all, eng.v_all, d_agg, lse2, pgs, plan, pg.num_kv_nodes, f, d, h, bws, compute, d_qkv,
                             send_slot, lambda t, slot: eng.push_backward(t, slot, compute))
             TIMER.mark("bwd attention dQ + dK|dV (ring phases, dK|dV pushes overlapped)")
             for t in range(1, world):
                 eng.wait_flag(plan.bwd_src[t], 1, bws, compute)
             if pg.add_tgt.numel():
-                _lib.call("ampconv_halo_add_bf16", eng.recv, pg.add_tgt, pg.add_rowptr, pg.add_pos, d_kv,
-                          _lib.i64(pg.add_tgt.numel()), _lib.i64(f * 2 * d), st)
+                _lib.call("ampconv_halo_add_bf16_strided", eng.recv, pg.add_tgt, pg.add_rowptr, pg.add_pos, d_qkv,
+                          _lib.i64(pg.add_tgt.numel()), _lib.i64(f * 2 * d), _lib.i64(2 * d), _lib.i64(3 * d), _lib.i64(d), st)
             TIMER.mark("bwd wait for peers' dK|dV blocks + fixed-order add")
-            d_qkv = torch.cat([d_q, d_kv], dim=1)
             d_x = torch.empty_like(x_local)
             d_w_in = torch.empty_like(w_in)
             d_b_in = torch.empty(3 * d, dtype=torch.float32, device=dev)

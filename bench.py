@@ -291,7 +291,8 @@ def run_ours(args):
     torch.cuda.set_device(dev)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
     spec = dict(WORKLOADS[args.workload])
     n, e, f, d, h = spec["n"], spec["e"], spec["f"], spec["d"], spec["h"]
 

@@ -297,8 +297,10 @@ AMPCONV_API int ampconv_halo_add_bf16(const void* recv_bf16, const int32_t* tgt,
  * and is one launch over the `n_work` nodes listed in `order`.  lse2 / delta are indexed by the phase's own slots.
  *   fwd / dq : accumulate = 0 -> first phase executed (overwrites; destinations without an edge are zero-filled),
  *              accumulate = 1 -> adds to agg / d_q (destinations without an edge in the phase are not in `order`);
- *   dkv      : own sources (d_kv_halo NULL) -> d_kv_own fp32 [num_own*F, 128]; the phase owner's halo sources, compact ids
- *              [halo_from, ...) -> bf16 rows d_kv_halo[(id - halo_from)*F, 128], the block that travels to that owner. */
+ *   dq       : row r of the result at d_q[r * d_q_ld] (a dense [rows, 64] tensor or the first columns of d_qkv [rows, 192]);
+ *   dkv      : own sources (d_kv_halo NULL) -> d_kv_own fp32, row r at d_kv_own[r * own_ld], dK at column own_dk_col and dV
+ *              at own_dv_col; the phase owner's halo sources, compact ids [halo_from, ...) (d_kv_own NULL) -> bf16 rows
+ *              d_kv_halo[(id - halo_from)*F, 128] = dK | dV, the block that travels to that owner. */
 AMPCONV_API int ampconv_attn_fwd_bf16_phase(const void* q, const void* k, const void* v,
                                 const int32_t* dst_rowptr, const int32_t* dst_src, const float* inv_deg,
                                 const int32_t* order, int64_t n_work, int accumulate, float* agg, float* lse2,
@@ -306,13 +308,15 @@ AMPCONV_API int ampconv_attn_fwd_bf16_phase(const void* q, const void* k, const 
                                 int F, int d, int H, void* workspace, size_t workspace_bytes, void* stream);
 AMPCONV_API int ampconv_attn_bwd_dq_bf16_phase(const void* q, const void* k, const void* v, const void* d_agg_bf16,
                                    const float* lse2, const int32_t* dst_rowptr, const int32_t* dst_src,
-                                   const int32_t* order, int64_t n_work, int accumulate, float* d_q, float* delta,
+                                   const int32_t* order, int64_t n_work, int accumulate, float* d_q, int64_t d_q_ld,
+                                   float* delta,
                                    int64_t num_nodes, int64_t num_kv_nodes, int64_t num_edges, int F, int d, int H,
                                    void* workspace, size_t workspace_bytes, void* stream);
 AMPCONV_API int ampconv_attn_bwd_dkv_bf16_phase(const void* q, const void* k, const void* v, const void* d_agg_bf16,
                                     const float* lse2, const float* delta, const int32_t* src_rowptr,
                                     const int32_t* src_dst, const int32_t* src_pos, const int32_t* order,
-                                    int64_t n_work, float* d_kv_own, void* d_kv_halo, int64_t halo_from,
+                                    int64_t n_work, float* d_kv_own, int64_t own_ld, int64_t own_dk_col, int64_t own_dv_col,
+                                    void* d_kv_halo, int64_t halo_from,
                                     int64_t num_nodes, int64_t num_kv_nodes, int64_t num_edges, int F, int d, int H,
                                     void* workspace, size_t workspace_bytes, void* stream);
 
@@ -343,6 +347,12 @@ AMPCONV_API int ampconv_peer_signal(int32_t* peer_flag, const int32_t* ramp, int
 AMPCONV_API int ampconv_peer_wait(const int32_t* flag, int32_t expected, void* workspace, double budget_seconds, void* stream);
 AMPCONV_API int ampconv_gather_rows(const void* src, const int64_t* idx, void* dst, int64_t n_rows, int64_t row_bytes,
                         void* stream);
+
+/* ampconv_halo_add_bf16 into a strided accumulator: a received row holds row_elems / tok_elems token rows; token row t of node
+ * n is acc[(n * tokens + t) * acc_ld + acc_col ...] -- e.g. the dK | dV columns [d, 3d) of one d_qkv [rows, 3d] tensor. */
+AMPCONV_API int ampconv_halo_add_bf16_strided(const void* recv_bf16, const int32_t* tgt, const int32_t* rowptr, const int32_t* pos,
+                                  float* acc, int64_t n_tgt, int64_t row_elems, int64_t tok_elems, int64_t acc_ld,
+                                  int64_t acc_col, void* stream);
 
 /* Copies the status word of the last bf16 kernel that used `workspace` to the host (0 = ok, otherwise
  * the id of the pipeline wait that timed out).  Synchronises `stream`; meant for tests and debugging. */

@@ -20,10 +20,12 @@ def _worker(rank, world, port, spec, transport, ret):
     from ampnet_b200 import AMPConv, distributed as D
     from ampnet_b200 import functional as F_
     from oracle import cases, numpy_oracle
+    import datetime
+    import traceback
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dev = torch.device("cuda", rank)
     torch.cuda.set_device(dev)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev, timeout=datetime.timedelta(seconds=90))
     try:
         n, e, f, d, h = spec
         x, ei, p, d_out = cases.make_inputs(n, e, f, d, h, graph="skewed", seed=31)
@@ -57,8 +59,11 @@ def _worker(rank, world, port, spec, transport, ret):
                 errs[f"{name}{it}"] = rel(q.grad.cpu().numpy(), ref[name], ref[name])
         ret[rank] = errs
         D.close_engines()
-    finally:
         dist.destroy_process_group()
+    except BaseException:
+        # a rank that fails must not wait for its peers (destroy_process_group would): die at once so that the parent sees it
+        traceback.print_exc()
+        os._exit(1)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs at least 2 GPUs")

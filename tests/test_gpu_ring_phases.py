@@ -81,8 +81,7 @@ def _virtual_world_layer(x, ei, p, d_out, h, world, dev):
                   _lib.i32(d), pws, _lib.size_t(pws.numel()), ws, st)
         grads[2] += d_w_out
         grads[3] += d_b_out
-        r["d_q"] = torch.empty((rows, d), dtype=torch.float32, device=dev)
-        r["d_kv"] = torch.empty((rows, 2 * d), dtype=torch.float32, device=dev)
+        r["d_qkv"] = torch.empty((rows, 3 * d), dtype=torch.float32, device=dev)
         bufs = {}
 
         def send_slot(t, plan=plan, bufs=bufs):
@@ -94,15 +93,15 @@ def _virtual_world_layer(x, ei, p, d_out, h, world, dev):
             owner["recv"][off:off + cnt] = bufs[slot][:cnt]
 
         D.backward_phases(r["q"], r["k"], r["v"], r["d_agg"], r["lse2"], g, plan, pg.num_kv_nodes, f, d, h, ws, stream,
-                          r["d_q"], r["d_kv"], send_slot, ship)
+                          r["d_qkv"], send_slot, ship)
     d_x = torch.empty((n, width), dtype=torch.float32, device=dev)
     for r in R:
         pg = r["pg"]
         rows = pg.n_local * f
         if pg.add_tgt.numel():
-            _lib.call("ampconv_halo_add_bf16", r["recv"], pg.add_tgt, pg.add_rowptr, pg.add_pos, r["d_kv"],
-                      _lib.i64(pg.add_tgt.numel()), _lib.i64(f * 2 * d), st)
-        d_qkv = torch.cat([r["d_q"], r["d_kv"]], dim=1)
+            _lib.call("ampconv_halo_add_bf16_strided", r["recv"], pg.add_tgt, pg.add_rowptr, pg.add_pos, r["d_qkv"],
+                      _lib.i64(pg.add_tgt.numel()), _lib.i64(f * 2 * d), _lib.i64(2 * d), _lib.i64(3 * d), _lib.i64(d), st)
+        d_qkv = r["d_qkv"]
         d_w_in, d_b_in = torch.empty_like(w_in), torch.empty_like(b_in)
         _lib.call("ampconv_qkv_proj_bwd_input_tc", d_qkv, w_in, d_x[pg.lo:pg.hi], _lib.i64(rows), _lib.i32(d), ws, st)
         _lib.call("ampconv_qkv_proj_bwd_params_tc", r["x"], d_qkv, d_w_in, d_b_in, _lib.i64(rows), _lib.i32(d), pws,
