@@ -34,6 +34,7 @@ WORKLOADS = {
     "C4s": dict(n=16934, e=116624, f=128, d=64, h=4, desc="C4 token shape at 1/10 of the nodes and edges"),
     "C5": dict(n=2449029, e=61859140, f=100, d=64, h=8, desc="synthetic ogbn-products shape (multi-GPU only)"),
     "C5s": dict(n=122451, e=3092957, f=100, d=64, h=8, desc="ogbn-products token shape at 1/20 of the nodes and edges"),
+    "C5h": dict(n=1224514, e=30929570, f=100, d=64, h=8, desc="ogbn-products token shape at 1/2 of the nodes and edges (8 GPUs)"),
 }
 METRIC = "AMPConv fwd+bwd edges/sec"
 
