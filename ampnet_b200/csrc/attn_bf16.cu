@@ -520,8 +520,8 @@ static int attn_fwd_bf16_impl(const void* q, const void* k, const void* v,
   AMPCONV_REQUIRE(N >= 0 && E >= 0 && F > 0 && d > 0 && H > 0 && d % H == 0);
   if (!ampconv_attn_bf16_supported(F, d, H)) return AMPCONV_ERR_UNSUPPORTED;
   if (n_work < 0) n_work = N;        // length of the `order` work list (all destinations unless a ring phase lists fewer)
-  AMPCONV_REQUIRE(n_work <= N && (n_work == N || order != nullptr));
   if (N == 0 || n_work == 0) return AMPCONV_OK;
+  AMPCONV_REQUIRE(n_work <= N && (n_work == N || order != nullptr));
   AMPCONV_REQUIRE(q && k && v && dst_rowptr && inv_deg && agg && workspace && (E == 0 || (dst_src && lse2)));
   if (workspace_bytes < 256) return AMPCONV_ERR_WORKSPACE;
   cudaStream_t stream = as_stream(stream_);
@@ -601,7 +601,7 @@ extern "C" int ampconv_attn_fwd_bf16_phase(const void* q, const void* k, const v
                                            int64_t num_nodes, int64_t num_kv_nodes, int64_t E,
                                            int F, int d, int H, void* workspace, size_t workspace_bytes, void* stream_) {
   AMPCONV_REQUIRE(num_kv_nodes > 0 || E == 0);
-  AMPCONV_REQUIRE(n_work >= 0 && order != nullptr);
+  AMPCONV_REQUIRE(n_work >= 0 && (order != nullptr || n_work == 0));
   return attn_fwd_bf16_impl(q, k, v, dst_rowptr, dst_src, inv_deg, order, agg, lse2, num_nodes,
                             num_kv_nodes > 0 ? num_kv_nodes : 1, E, F, d, H, workspace, workspace_bytes, stream_, nullptr,
                             n_work, accumulate);

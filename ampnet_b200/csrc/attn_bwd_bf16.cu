@@ -146,8 +146,8 @@ __global__ void __launch_bounds__(threads_of(MODE), 1)
 attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_constant__ CUtensorMap own1,
                      const __grid_constant__ CUtensorMap oth0, const __grid_constant__ CUtensorMap oth1,
                      const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr,
-                     const int32_t* __restrict__ slot_of, const int32_t* __restrict__ order,
-                     const float* __restrict__ lse2, float* __restrict__ delta, float* __restrict__ d_qkv, int* __restrict__ counter, int* __restrict__ status,
+                     const int32_t* __restrict__ slot_of, const int32_t* __restrict__ lse_map,
+                     const int32_t* __restrict__ order, const float* __restrict__ lse2, float* __restrict__ delta, float* __restrict__ d_qkv, int* __restrict__ counter, int* __restrict__ status,
                      int N, int F, float out_scale0, float out_scale1, int out_ld, int out_c0, int out_c1,
                      uint16_t* __restrict__ halo_bf16, int halo_from, int accumulate,
                      const uint8_t* __restrict__ gown0, const uint8_t* __restrict__ gown1,
@@ -283,14 +283,18 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
                 failed = 102;
                 break;
               }
+              // statistics of the edge: delta lives at the pass's slot of the edge, lse2 where the FORWARD wrote it
+              // (lse_map: slot -> forward index; the forward may have run finer ring phases than this pass)
               if (MODE == MODE_DKV) {
                 const int64_t sl = slot_of ? slot_of[e] : e;
+                const int64_t le = lse_map ? lse_map[sl] : sl;
                 mbar_arrive_expect_tx(&sm.edge_full[st], 2 * kTileBytes + 2 * stat_bytes);
-                bulk_load(sm.stat[st][0], lse2 + (sl * HT + grp * H) * Fs, stat_bytes, &sm.edge_full[st]);
+                bulk_load(sm.stat[st][0], lse2 + (le * HT + grp * H) * Fs, stat_bytes, &sm.edge_full[st]);
                 bulk_load(sm.stat[st][1], delta + (sl * HT + grp * H) * Fs, stat_bytes, &sm.edge_full[st]);
               } else {
+                const int64_t le = lse_map ? lse_map[e] : e;
                 mbar_arrive_expect_tx(&sm.edge_full[st], 2 * kTileBytes + stat_bytes);
-                bulk_load(sm.stat[st][0], lse2 + ((int64_t)e * HT + grp * H) * Fs, stat_bytes, &sm.edge_full[st]);
+                bulk_load(sm.stat[st][0], lse2 + (le * HT + grp * H) * Fs, stat_bytes, &sm.edge_full[st]);
               }
               tma_load_3d(sm.edge[st][0], &oth0, &sm.edge_full[st], 0, 0, nb);
               tma_load_3d(sm.edge[st][1], &oth1, &sm.edge_full[st], 0, 0, nb);
@@ -376,12 +380,14 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
             failed = 102;
           } else if (MODE == MODE_DKV) {
             const int64_t sl = slot_of ? slot_of[e] : e;
+            const int64_t le = lse_map ? lse_map[sl] : sl;
             mbar_arrive_expect_tx(&sm.edge_full[st], 2 * stat_bytes);
-            bulk_load(sm.stat[st][0], lse2 + (sl * HT + grp * H) * Fs, stat_bytes, &sm.edge_full[st]);
+            bulk_load(sm.stat[st][0], lse2 + (le * HT + grp * H) * Fs, stat_bytes, &sm.edge_full[st]);
             bulk_load(sm.stat[st][1], delta + (sl * HT + grp * H) * Fs, stat_bytes, &sm.edge_full[st]);
           } else {
+            const int64_t le = lse_map ? lse_map[e] : e;
             mbar_arrive_expect_tx(&sm.edge_full[st], stat_bytes);
-            bulk_load(sm.stat[st][0], lse2 + ((int64_t)e * HT + grp * H) * Fs, stat_bytes, &sm.edge_full[st]);
+            bulk_load(sm.stat[st][0], lse2 + (le * HT + grp * H) * Fs, stat_bytes, &sm.edge_full[st]);
           }
         }
         failed = __shfl_sync(0xffffffffu, failed, 0);
@@ -860,8 +866,8 @@ long long* g_bwd_prof = nullptr;   // debug: set through ampconv_debug_set_bwd_p
 template <int HD, int MODE, int GROUPS>
 int launch_bwd(const CUtensorMap& own0, const CUtensorMap& own1, const CUtensorMap& oth0, const CUtensorMap& oth1,
                const void* gown0, const void* gown1, const void* goth0, const void* goth1,
-               const int32_t* rowptr, const int32_t* nbr, const int32_t* slot_of, const int32_t* order, const float* lse2,
-               float* delta, float* d_qkv, int* counter, int* status, int N, int F, float s0, float s1, int out_ld, int out_c0,
+               const int32_t* rowptr, const int32_t* nbr, const int32_t* slot_of, const int32_t* lse_map, const int32_t* order,
+               const float* lse2, float* delta, float* d_qkv, int* counter, int* status, int N, int F, float s0, float s1, int out_ld, int out_c0,
                int out_c1, uint16_t* halo_bf16, int halo_from, int accumulate, cudaStream_t stream) {
   const size_t smem = sizeof(BwdSmem<MODE>) + 1024;
   const int items = N * GROUPS;
@@ -872,7 +878,7 @@ int launch_bwd(const CUtensorMap& own0, const CUtensorMap& own1, const CUtensorM
     AMPCONV_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_bf16_kernel<HD, MODE, NH_, GROUPS, PROF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                           (int)smem));                                                                           \
     attn_bwd_bf16_kernel<HD, MODE, NH_, GROUPS, PROF_><<<grid, threads_of(MODE), smem, stream>>>(                                         \
-        own0, own1, oth0, oth1, rowptr, nbr, slot_of, order, lse2, delta, d_qkv, counter, status, N, F, s0, s1, out_ld, out_c0,   \
+        own0, own1, oth0, oth1, rowptr, nbr, slot_of, lse_map, order, lse2, delta, d_qkv, counter, status, N, F, s0, s1, out_ld, out_c0,   \
         out_c1, halo_bf16, halo_from, accumulate, reinterpret_cast<const uint8_t*>(gown0),                                      \
         reinterpret_cast<const uint8_t*>(gown1), reinterpret_cast<const uint8_t*>(goth0),                                       \
         reinterpret_cast<const uint8_t*>(goth1), prof_);                                                                                  \
@@ -902,13 +908,13 @@ static int bwd_common(int mode, const void* q, const void* k, const void* v, con
                       const int32_t* rowptr, const int32_t* nbr, const int32_t* slot_of, const int32_t* order,
                       const float* lse2, float* delta, float* out, int out_ld, int out_c0, int out_c1, int64_t N_dst, int64_t N_kv, int64_t E, int F, int d,
                       int H, void* workspace, size_t workspace_bytes, void* stream_, void* halo_bf16 = nullptr,
-                      int64_t halo_from = 0, int64_t n_work = -1, int accumulate = 0) {
+                      int64_t halo_from = 0, int64_t n_work = -1, int accumulate = 0, const int32_t* lse_map = nullptr) {
   AMPCONV_REQUIRE(N_dst >= 0 && N_kv >= 0 && E >= 0 && F > 0 && d > 0 && H > 0 && d % H == 0);
   if (!ampconv_attn_bf16_supported(F, d, H)) return AMPCONV_ERR_UNSUPPORTED;
   const int64_t N_own = mode == MODE_DQ ? N_dst : N_kv;
   if (n_work < 0) n_work = N_own;
-  AMPCONV_REQUIRE(n_work <= N_own && (n_work == N_own || order != nullptr));
   if (N_own == 0 || n_work == 0) return AMPCONV_OK;
+  AMPCONV_REQUIRE(n_work <= N_own && (n_work == N_own || order != nullptr));
   AMPCONV_REQUIRE(q && k && v && d_agg_bf16 && rowptr && workspace && (out || halo_bf16));
   AMPCONV_REQUIRE(E == 0 || (nbr && lse2 && delta));
   if (workspace_bytes < 256) return AMPCONV_ERR_WORKSPACE;
@@ -927,22 +933,22 @@ static int bwd_common(int mode, const void* q, const void* k, const void* v, con
   if (mode == MODE_DQ) {
     // dQ = hd^-1/2 * (dS K)
     if (hd == 8)
-      return launch_bwd<16, MODE_DQ, 2>(mq, mg, mk, mv, q, d_agg_bf16, k, v, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)n_work, F,
+      return launch_bwd<16, MODE_DQ, 2>(mq, mg, mk, mv, q, d_agg_bf16, k, v, rowptr, nbr, slot_of, lse_map, order, lse2, delta, out, counter, status, (int)n_work, F,
                                        inv_sqrt_hd, 0.f, out_ld, out_c0, out_c1, nullptr, 0, accumulate, stream);
     if (hd == 16)
-      return launch_bwd<16, MODE_DQ, 1>(mq, mg, mk, mv, q, d_agg_bf16, k, v, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)n_work, F,
+      return launch_bwd<16, MODE_DQ, 1>(mq, mg, mk, mv, q, d_agg_bf16, k, v, rowptr, nbr, slot_of, lse_map, order, lse2, delta, out, counter, status, (int)n_work, F,
                                     inv_sqrt_hd, 0.f, out_ld, out_c0, out_c1, nullptr, 0, accumulate, stream);
-    return launch_bwd<32, MODE_DQ, 1>(mq, mg, mk, mv, q, d_agg_bf16, k, v, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)n_work, F,
+    return launch_bwd<32, MODE_DQ, 1>(mq, mg, mk, mv, q, d_agg_bf16, k, v, rowptr, nbr, slot_of, lse_map, order, lse2, delta, out, counter, status, (int)n_work, F,
                                   inv_sqrt_hd, 0.f, out_ld, out_c0, out_c1, nullptr, 0, accumulate, stream);
   }
   // dK = hd^-1/2 * dS^T Q = ln2 * dS^T Q'  (Q' = Q * log2e / sqrt(hd)),  dV = P^T dO
   if (hd == 8)
-    return launch_bwd<16, MODE_DKV, 2>(mk, mv, mq, mg, k, v, q, d_agg_bf16, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)n_work, F,
+    return launch_bwd<16, MODE_DKV, 2>(mk, mv, mq, mg, k, v, q, d_agg_bf16, rowptr, nbr, slot_of, lse_map, order, lse2, delta, out, counter, status, (int)n_work, F,
                                       ln2, 1.f, out_ld, out_c0, out_c1, reinterpret_cast<uint16_t*>(halo_bf16), (int)halo_from, 0, stream);
   if (hd == 16)
-    return launch_bwd<16, MODE_DKV, 1>(mk, mv, mq, mg, k, v, q, d_agg_bf16, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)n_work, F,
+    return launch_bwd<16, MODE_DKV, 1>(mk, mv, mq, mg, k, v, q, d_agg_bf16, rowptr, nbr, slot_of, lse_map, order, lse2, delta, out, counter, status, (int)n_work, F,
                                    ln2, 1.f, out_ld, out_c0, out_c1, reinterpret_cast<uint16_t*>(halo_bf16), (int)halo_from, 0, stream);
-  return launch_bwd<32, MODE_DKV, 1>(mk, mv, mq, mg, k, v, q, d_agg_bf16, rowptr, nbr, slot_of, order, lse2, delta, out, counter, status, (int)n_work, F, ln2,
+  return launch_bwd<32, MODE_DKV, 1>(mk, mv, mq, mg, k, v, q, d_agg_bf16, rowptr, nbr, slot_of, lse_map, order, lse2, delta, out, counter, status, (int)n_work, F, ln2,
                                  1.f, out_ld, out_c0, out_c1, reinterpret_cast<uint16_t*>(halo_bf16), (int)halo_from, 0, stream);
 }
 
@@ -1008,33 +1014,36 @@ extern "C" int ampconv_attn_bwd_dkv_bf16_halo(const void* q, const void* k, cons
 //               phase's owner, compact ids [halo_from, ...), go as bf16 rows to d_kv_halo[(id - halo_from)*F, 128]: the
 //               block that travels to that owner.
 extern "C" int ampconv_attn_bwd_dq_bf16_phase(const void* q, const void* k, const void* v, const void* d_agg_bf16,
-                                              const float* lse2, const int32_t* dst_rowptr, const int32_t* dst_src,
+                                              const float* lse2, const int32_t* lse_map, const int32_t* dst_rowptr,
+                                              const int32_t* dst_src,
                                               const int32_t* order, int64_t n_work, int accumulate, float* d_q, int64_t d_q_ld,
                                               float* delta,
                                               int64_t num_nodes, int64_t num_kv_nodes, int64_t E, int F, int d, int H,
                                               void* workspace, size_t workspace_bytes, void* stream) {
-  AMPCONV_REQUIRE(n_work >= 0 && order != nullptr && d_q_ld >= kD && d_q_ld % 4 == 0);
+  AMPCONV_REQUIRE(n_work >= 0 && (order != nullptr || n_work == 0) && d_q_ld >= kD && d_q_ld % 4 == 0);
   return bwd_common(MODE_DQ, q, k, v, d_agg_bf16, dst_rowptr, dst_src, nullptr, order, lse2, delta, d_q, (int)d_q_ld, 0, 0, num_nodes,
-                    num_kv_nodes, E, F, d, H, workspace, workspace_bytes, stream, nullptr, 0, n_work, accumulate);
+                    num_kv_nodes, E, F, d, H, workspace, workspace_bytes, stream, nullptr, 0, n_work, accumulate, lse_map);
 }
 
 extern "C" int ampconv_attn_bwd_dkv_bf16_phase(const void* q, const void* k, const void* v, const void* d_agg_bf16,
-                                               const float* lse2, const float* delta, const int32_t* src_rowptr,
+                                               const float* lse2, const int32_t* lse_map, const float* delta,
+                                               const int32_t* src_rowptr,
                                                const int32_t* src_dst, const int32_t* src_pos, const int32_t* order,
                                                int64_t n_work, float* d_kv_own, int64_t own_ld, int64_t own_dk_col,
                                                int64_t own_dv_col, void* d_kv_halo, int64_t halo_from,
                                                int64_t num_nodes, int64_t num_kv_nodes, int64_t E, int F, int d, int H,
                                                void* workspace, size_t workspace_bytes, void* stream) {
-  AMPCONV_REQUIRE(n_work >= 0 && order != nullptr && halo_from >= 0 && ((d_kv_own != nullptr) != (d_kv_halo != nullptr)));
+  if (n_work == 0) return AMPCONV_OK;
+  AMPCONV_REQUIRE(n_work > 0 && order != nullptr && halo_from >= 0 && ((d_kv_own != nullptr) != (d_kv_halo != nullptr)));
   if (d_kv_halo != nullptr)      // a halo phase: only the owner's bf16 block [*, 128] = dK | dV is written
     return bwd_common(MODE_DKV, q, k, v, d_agg_bf16, src_rowptr, src_dst, src_pos, order, lse2, const_cast<float*>(delta), nullptr,
                       2 * kD, 0, kD, num_nodes, num_kv_nodes, E, F, d, H, workspace, workspace_bytes, stream, d_kv_halo,
-                      halo_from, n_work, 0);
+                      halo_from, n_work, 0, lse_map);
   AMPCONV_REQUIRE(own_ld >= 2 * kD && own_ld % 4 == 0 && own_dk_col % 4 == 0 && own_dv_col % 4 == 0 && own_dk_col + kD <= own_ld &&
                   own_dv_col + kD <= own_ld);
   return bwd_common(MODE_DKV, q, k, v, d_agg_bf16, src_rowptr, src_dst, src_pos, order, lse2, const_cast<float*>(delta), d_kv_own,
                     (int)own_ld, (int)own_dk_col, (int)own_dv_col, num_nodes, num_kv_nodes, E, F, d, H, workspace, workspace_bytes,
-                    stream, nullptr, num_kv_nodes, n_work, 0);
+                    stream, nullptr, num_kv_nodes, n_work, 0, lse_map);
 }
 
 // Debug: when set to a device buffer of 64 int64, the next backward launches run the instrumented kernel and fill it

@@ -144,7 +144,7 @@ extern "C" int ampconv_graph_build_bipartite(const int64_t* edge_index, int64_t 
                                    float* inv_deg, float* has_in,
                                    void* workspace, size_t workspace_bytes, void* stream_) {
   AMPCONV_REQUIRE(E >= 0 && N >= 0 && N_src >= 0 && E < (int64_t)INT32_MAX && N < (int64_t)INT32_MAX && N_src < (int64_t)INT32_MAX);
-  AMPCONV_REQUIRE(dst_rowptr && src_rowptr && inv_deg && has_in && workspace);
+  AMPCONV_REQUIRE(dst_rowptr && src_rowptr && workspace && (N == 0 || (inv_deg && has_in)));   // a rank may own no destination
   AMPCONV_REQUIRE(E == 0 || (edge_index && dst_src && dst_eid && src_dst && src_pos));
   cudaStream_t stream = as_stream(stream_);
   GraphWs ws;

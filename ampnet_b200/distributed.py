@@ -267,6 +267,29 @@ class PhaseGraphs:
         self.inv_deg = (1.0 / full.clamp(min=1).to(torch.float32)).contiguous()
         self.has_in = (full > 0).to(torch.float32).contiguous()
         self.max_phase_edges = max(g.num_edges for g in self.graphs)
+        # the forward's lse2 is ONE tensor: phase t's block starts at edge offset lse_off[t] (its own destination-sorted slots)
+        self.lse_off = [0]
+        for g in self.graphs:
+            self.lse_off.append(self.lse_off[-1] + g.num_edges)
+        # coarse view for the backward (a destination appears once, not once per owner): ALL halo edges in one dQ launch, the
+        # dK|dV launches per owner pick their sources from the same views.  halo_lse_map[slot] = forward lse2 index.
+        self.halo = None
+        if plan.world > 2:
+            dev = lei.device
+            fwd_index = torch.empty(lei.shape[1], dtype=torch.int64, device=dev)      # local edge -> forward lse2 index
+            for t, (g, sel) in enumerate(zip(self.graphs, self.edge_sel)):
+                if g.num_edges:
+                    fwd_index[sel[g.dst_eid.to(torch.int64)]] = self.lse_off[t] + torch.arange(g.num_edges, device=dev)
+            sel_h = torch.nonzero(ph != 0, as_tuple=False).squeeze(1)
+            gh = BipartiteGraph(lei[:, sel_h].contiguous(), pg.n_local, pg.num_kv_nodes)
+            self.halo = gh
+            self.halo_lse_map = (fwd_index[sel_h[gh.dst_eid.to(torch.int64)]].to(torch.int32).contiguous()
+                                 if gh.num_edges else torch.zeros(1, dtype=torch.int32, device=dev))
+            self.halo_order_src = [None]
+            for t in range(1, plan.world):
+                lo, hi = plan.src_range[t]
+                sdeg = gh.src_rowptr[lo + 1:hi + 1] - gh.src_rowptr[lo:hi]
+                self.halo_order_src.append((lo + torch.argsort(sdeg, descending=True)).to(torch.int32).contiguous())
 
 
 # ------------------------------------------------------------------------------------------ collectives (NCCL or gloo)
@@ -448,21 +471,19 @@ class _DistAMPConvFunction(torch.autograd.Function):
 
 def forward_phases(q, k_all, v_all, pgs, num_kv_nodes, f, d, h, ws, stream, agg, before_phase=None, after_phase=None):
     """The ring phases of the forward attention on `stream`: phase 0 (own sources) overwrites agg, phases 1.. add to it;
-    before_phase(t) is called right before phase t >= 1 is launched (the peer path waits there for the phase's K|V rows).
-    Returns the per-phase lse2 tensors."""
+    before_phase(t) is called right before phase t >= 1 is launched (the peer path waits there for the phase's K|V rows),
+    after_phase(t) right after.  Returns lse2 [E_local, H, roundup4(F)]: phase t's block at edge offset pgs.lse_off[t]."""
     n = agg.shape[0] // f
     fs = (f + 3) // 4 * 4
     st = _lib.stream_ptr(stream)
-    lse2 = []
+    lse2 = torch.empty((max(pgs.lse_off[-1], 1), h, fs), dtype=torch.float32, device=agg.device)
     for t in range(len(pgs.graphs)):
         g = pgs.graphs[t]
-        l2 = torch.empty((max(g.num_edges, 1), h, fs), dtype=torch.float32, device=agg.device)
-        lse2.append(l2)
         if t > 0 and before_phase is not None:
             before_phase(t)
         n_work = n if t == 0 else pgs.n_dst_active[t]
         _lib.call("ampconv_attn_fwd_bf16_phase", q, k_all, v_all, g.dst_rowptr, g.dst_src, pgs.inv_deg,
-                  pgs.order_dst[t], _lib.i64(n_work), _lib.i32(0 if t == 0 else 1), agg, l2,
+                  pgs.order_dst[t], _lib.i64(n_work), _lib.i32(0 if t == 0 else 1), agg, lse2[pgs.lse_off[t]:],
                   _lib.i64(n), _lib.i64(num_kv_nodes), _lib.i64(g.num_edges), _lib.i32(f), _lib.i32(d),
                   _lib.i32(h), ws, _lib.size_t(256), st)
         if after_phase is not None:
@@ -470,41 +491,66 @@ def forward_phases(q, k_all, v_all, pgs, num_kv_nodes, f, d, h, ws, stream, agg,
     return lse2
 
 
+COARSE_DELTA_BUDGET_BYTES = 16 << 30     # the coarse backward holds delta for all halo edges at once
+
+
 def backward_phases(q, k_all, v_all, d_agg, lse2, pgs, plan, num_kv_nodes, f, d, h, ws, stream, d_qkv, send_slot,
                     after_halo_phase):
-    """The ring phases of the attention backward on `stream`: per phase dQ (first executed phase overwrites, the others add)
-    then dK|dV of the phase's sources; halo phases first -- send_slot(t) -> (slot, bf16 buffer) receives the phase owner's
-    block and after_halo_phase(t, slot) ships it -- own sources last.  d_qkv fp32 [rows, 3d] = dQ | dK | dV of the own rows."""
+    """The attention backward of a rank on `stream`, halo sources first (their dK|dV blocks travel while the rest computes),
+    own sources last.  d_qkv fp32 [rows, 3d] = dQ | dK | dV of the own rows; send_slot(t) -> (slot, bf16 buffer) receives the
+    block of ring phase t's owner and after_halo_phase(t, slot) ships it.
+
+    Coarse schedule (default when delta for all halo edges fits): ONE dQ launch over all halo edges -- a destination is
+    visited once instead of once per owner -- then dK|dV per owner out of the same views, then dQ / dK|dV of the own-source
+    edges.  Fine schedule: dQ and dK|dV per ring phase (delta only ever holds one phase)."""
     n = d_qkv.shape[0] // f
     fs = (f + 3) // 4 * 4
     st = _lib.stream_ptr(stream)
     world = len(pgs.graphs)
-    delta = torch.empty((max(pgs.max_phase_edges, 1), h, fs), dtype=torch.float32, device=d_qkv.device)
+    dev = d_qkv.device
+    tail = (_lib.i64(n), _lib.i64(num_kv_nodes))
+    shp = (_lib.i32(f), _lib.i32(d), _lib.i32(h), ws, _lib.size_t(256), st)
+
+    def dq(g, lse, lse_map, order, n_work, accumulate, delta):
+        _lib.call("ampconv_attn_bwd_dq_bf16_phase", q, k_all, v_all, d_agg, lse, lse_map, g.dst_rowptr, g.dst_src,
+                  order, _lib.i64(n_work), _lib.i32(accumulate), d_qkv, _lib.i64(3 * d), delta, *tail, _lib.i64(g.num_edges), *shp)
+
+    def dkv_halo(g, lse, lse_map, delta, order, lo, hi, buf):
+        _lib.call("ampconv_attn_bwd_dkv_bf16_phase", q, k_all, v_all, d_agg, lse, lse_map, delta, g.src_rowptr, g.src_dst,
+                  g.src_pos, order, _lib.i64(hi - lo), None, _lib.i64(0), _lib.i64(0), _lib.i64(0), buf, _lib.i64(lo),
+                  *tail, _lib.i64(g.num_edges), *shp)
+
+    coarse = pgs.halo is not None and pgs.halo.num_edges * h * fs * 4 <= COARSE_DELTA_BUDGET_BYTES
     first = True
-    for t in list(range(1, world)) + [0]:
+    if coarse:
+        gh = pgs.halo
+        delta = torch.empty((max(gh.num_edges, 1), h, fs), dtype=torch.float32, device=dev)
+        dq(gh, lse2, pgs.halo_lse_map, gh.order_dst, n, 0, delta)
+        first = False
+        for t in range(1, world):
+            lo, hi = plan.src_range[t]
+            slot, buf = send_slot(t)
+            if hi > lo:
+                dkv_halo(gh, lse2, pgs.halo_lse_map, delta, pgs.halo_order_src[t], lo, hi, buf)
+            after_halo_phase(t, slot)      # an empty block still raises its flag
+        del delta
+    delta = torch.empty((max(pgs.max_phase_edges if not coarse else pgs.graphs[0].num_edges, 1), h, fs), dtype=torch.float32,
+                        device=dev)
+    for t in ([] if coarse else list(range(1, world))) + [0]:
         g = pgs.graphs[t]
-        n_work = n if first else pgs.n_dst_active[t]
-        _lib.call("ampconv_attn_bwd_dq_bf16_phase", q, k_all, v_all, d_agg, lse2[t], g.dst_rowptr, g.dst_src,
-                  pgs.order_dst[t], _lib.i64(n_work), _lib.i32(0 if first else 1), d_qkv, _lib.i64(3 * d), delta,
-                  _lib.i64(n), _lib.i64(num_kv_nodes), _lib.i64(g.num_edges), _lib.i32(f), _lib.i32(d), _lib.i32(h),
-                  ws, _lib.size_t(256), st)
+        lse_t = lse2[pgs.lse_off[t]:]
+        dq(g, lse_t, None, pgs.order_dst[t], n if first else pgs.n_dst_active[t], 0 if first else 1, delta)
         first = False
         lo, hi = plan.src_range[t]
         if t == 0:
-            _lib.call("ampconv_attn_bwd_dkv_bf16_phase", q, k_all, v_all, d_agg, lse2[t], delta, g.src_rowptr,
+            _lib.call("ampconv_attn_bwd_dkv_bf16_phase", q, k_all, v_all, d_agg, lse_t, None, delta, g.src_rowptr,
                       g.src_dst, g.src_pos, pgs.order_src[t], _lib.i64(hi - lo), d_qkv, _lib.i64(3 * d), _lib.i64(d),
-                      _lib.i64(2 * d), None, _lib.i64(num_kv_nodes),
-                      _lib.i64(n), _lib.i64(num_kv_nodes), _lib.i64(g.num_edges), _lib.i32(f), _lib.i32(d), _lib.i32(h),
-                      ws, _lib.size_t(256), st)
+                      _lib.i64(2 * d), None, _lib.i64(num_kv_nodes), *tail, _lib.i64(g.num_edges), *shp)
             continue
         slot, buf = send_slot(t)
         if hi > lo:
-            _lib.call("ampconv_attn_bwd_dkv_bf16_phase", q, k_all, v_all, d_agg, lse2[t], delta, g.src_rowptr,
-                      g.src_dst, g.src_pos, pgs.order_src[t], _lib.i64(hi - lo), None, _lib.i64(0), _lib.i64(0), _lib.i64(0),
-                      buf, _lib.i64(lo),
-                      _lib.i64(n), _lib.i64(num_kv_nodes), _lib.i64(g.num_edges), _lib.i32(f), _lib.i32(d), _lib.i32(h),
-                      ws, _lib.size_t(256), st)
-        after_halo_phase(t, slot)      # an empty block still raises its flag
+            dkv_halo(g, lse_t, None, delta, pgs.order_src[t], lo, hi, buf)
+        after_halo_phase(t, slot)
 
 
 # ------------------------------------------------------------------------------------------ peer-memory engine (CUDA, world > 1)

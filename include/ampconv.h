@@ -297,6 +297,9 @@ AMPCONV_API int ampconv_halo_add_bf16(const void* recv_bf16, const int32_t* tgt,
  * and is one launch over the `n_work` nodes listed in `order`.  lse2 / delta are indexed by the phase's own slots.
  *   fwd / dq : accumulate = 0 -> first phase executed (overwrites; destinations without an edge are zero-filled),
  *              accumulate = 1 -> adds to agg / d_q (destinations without an edge in the phase are not in `order`);
+ *   lse_map  : optional (NULL = identity): the backward may run over a COARSER edge set than the forward's phases (one dQ
+ *              launch over all halo edges, dK|dV per owner from the same views); lse_map[slot of this pass] = index of the
+ *              edge's statistics block in the forward's lse2; delta is always indexed by this pass's slots;
  *   dq       : row r of the result at d_q[r * d_q_ld] (a dense [rows, 64] tensor or the first columns of d_qkv [rows, 192]);
  *   dkv      : own sources (d_kv_halo NULL) -> d_kv_own fp32, row r at d_kv_own[r * own_ld], dK at column own_dk_col and dV
  *              at own_dv_col; the phase owner's halo sources, compact ids [halo_from, ...) (d_kv_own NULL) -> bf16 rows
@@ -307,13 +310,13 @@ AMPCONV_API int ampconv_attn_fwd_bf16_phase(const void* q, const void* k, const 
                                 int64_t num_nodes, int64_t num_kv_nodes, int64_t num_edges,
                                 int F, int d, int H, void* workspace, size_t workspace_bytes, void* stream);
 AMPCONV_API int ampconv_attn_bwd_dq_bf16_phase(const void* q, const void* k, const void* v, const void* d_agg_bf16,
-                                   const float* lse2, const int32_t* dst_rowptr, const int32_t* dst_src,
+                                   const float* lse2, const int32_t* lse_map, const int32_t* dst_rowptr, const int32_t* dst_src,
                                    const int32_t* order, int64_t n_work, int accumulate, float* d_q, int64_t d_q_ld,
                                    float* delta,
                                    int64_t num_nodes, int64_t num_kv_nodes, int64_t num_edges, int F, int d, int H,
                                    void* workspace, size_t workspace_bytes, void* stream);
 AMPCONV_API int ampconv_attn_bwd_dkv_bf16_phase(const void* q, const void* k, const void* v, const void* d_agg_bf16,
-                                    const float* lse2, const float* delta, const int32_t* src_rowptr,
+                                    const float* lse2, const int32_t* lse_map, const float* delta, const int32_t* src_rowptr,
                                     const int32_t* src_dst, const int32_t* src_pos, const int32_t* order,
                                     int64_t n_work, float* d_kv_own, int64_t own_ld, int64_t own_dk_col, int64_t own_dv_col,
                                     void* d_kv_halo, int64_t halo_from,

@@ -120,6 +120,7 @@ def _virtual_world_layer(x, ei, p, d_out, h, world, dev):
     dict(n=400, e=2500, f=100, d=64, h=4, graph="uniform", world=4),     # ragged token count
     dict(n=90, e=300, f=20, d=64, h=2, graph="uniform", world=8),        # head_dim 32; phases with very few (or no) edges
     dict(n=480, e=3000, f=100, d=64, h=8, graph="skewed", world=3),      # C5 token shape: head_dim 8, two head groups per node
+    dict(n=600, e=4200, f=128, d=64, h=4, graph="skewed", world=8),      # a hub holds > 1/8 of the edges: ranks that own no node
 ])
 def test_ring_phase_kernels_match_numpy_oracle(shape):
     from oracle import cases, numpy_oracle
