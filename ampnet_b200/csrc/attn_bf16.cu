@@ -37,7 +37,11 @@ constexpr int kD = 64;                 // embed dim of this kernel family (one 1
 constexpr int kTileBytes = 128 * 128;  // 128 tokens x 64 bf16
 constexpr int kStages = 5;             // K/V ring depth
 constexpr int kFwdThreads = 384;       // 2 softmax warpgroups + producer warp + 3 MMA-issuing warps
-constexpr bool kPolyShare = true;      // a quarter of the exponentials are evaluated on the FMA pipe (umma.cuh: ex2_poly2)
+#ifndef AMP_POLY_FWD
+#define AMP_POLY_FWD 1
+#endif
+// share of the exponentials evaluated on the FMA pipe (umma.cuh: ex2_poly2): 0 = none, 1 = a quarter, 2 = half
+constexpr int kPolyShare = AMP_POLY_FWD;
 
 struct NodeSlot {
   int node, p_begin, p_end;
@@ -411,7 +415,8 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
             const float2 b2 = f2add(make_float2(__uint_as_float(s[2 * j + 2]), __uint_as_float(s[2 * j + 3])), nm);
             const float2 ea = make_float2(ex2_approx(a2.x), ex2_approx(a2.y));
             // one pair in four goes to the FMA pipe instead of MUFU (kPolyShare, see ex2_poly2)
-            const float2 eb = (kPolyShare && (j & 2)) ? ex2_poly2(b2) : make_float2(ex2_approx(b2.x), ex2_approx(b2.y));
+            const float2 eb = (kPolyShare == 2 || (kPolyShare == 1 && (j & 2))) ? ex2_poly2(b2)
+                                                                                 : make_float2(ex2_approx(b2.x), ex2_approx(b2.y));
             la = f2add(la, ea);
             lb = f2add(lb, eb);
             pk[j] = pack_bf16x2(ea.x, ea.y);

@@ -51,13 +51,14 @@ constexpr int kAccCol = 384;     // accumulator block 0 at [384, 448), block 1 a
 constexpr int MODE_DQ = 0, MODE_DKV = 1;
 constexpr int kStatFloats = 4 * 128;   // H * roundup4(F) <= 512 floats per edge and statistic
 // Share of the exponentials evaluated on the FMA pipe (umma.cuh: ex2_poly2) instead of MUFU: every fourth pair of score
-// columns when enabled.  The forward gained 4 % from it; in these passes it is NOT measured yet, so the
-// switches stay off and the compiled kernels are unchanged.
+// columns when enabled.  Measured at C4 (profiles/r02_poly_share_ab.log): dK/dV 28.61 -> 28.07 ms with it, dQ 28.56 -> 29.32 ms
+// (its elementwise warps have no issue slots to spare), forward at a half share 26.2 -> 28.4 ms: these kernels are bound by
+// latency between the pipeline stages, not by MUFU throughput.
 #ifndef AMP_POLY_DQ
 #define AMP_POLY_DQ 0
 #endif
 #ifndef AMP_POLY_DKV
-#define AMP_POLY_DKV 0
+#define AMP_POLY_DKV 1
 #endif
 constexpr bool kPolyShareDq = AMP_POLY_DQ != 0, kPolyShareDkv = AMP_POLY_DKV != 0;
 

@@ -7,6 +7,5 @@ run() { # name, extra args...
   timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 8 "$@" > gpurun_out/g_${name}.json 2> gpurun_out/g_${name}.err; echo "${name} exit=$?" >> gpurun_out/g_${name}.err
 }
 run c4_peer --steps 5 --warmup 3
-AMPNET_B200_EXCHANGE=nccl run c4_nccl --steps 5 --warmup 3 --no-parity-check
-run c5h_peer --workload C5h --steps 3 --warmup 3 --no-parity-check
-for n in c4_peer c4_nccl c5h_peer; do grep -E "phase ms|exit=|Error|error|OutOfMemory" gpurun_out/g_${n}.err | tail -n 4; done
+run c5_peer --workload C5 --steps 3 --warmup 3 --no-parity-check
+for n in c4_peer c5_peer; do grep -E "phase ms|exit=|Error|error|OutOfMemory" gpurun_out/g_${n}.err | tail -n 4; done
