@@ -150,7 +150,7 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
                      const int32_t* __restrict__ slot_of, const int32_t* __restrict__ lse_map,
                      const int32_t* __restrict__ order, const float* __restrict__ lse2, float* __restrict__ delta, float* __restrict__ d_qkv, int* __restrict__ counter, int* __restrict__ status,
                      int N, int F, float out_scale0, float out_scale1, int out_ld, int out_c0, int out_c1,
-                     uint16_t* __restrict__ halo_bf16, int halo_from, int accumulate,
+                     uint16_t* __restrict__ halo_bf16, int halo_from, int accumulate, int out_bf16,
                      const uint8_t* __restrict__ gown0, const uint8_t* __restrict__ gown1,
                      const uint8_t* __restrict__ goth0, const uint8_t* __restrict__ goth1, long long* __restrict__ prof) {
   using Smem = BwdSmem<MODE>;
@@ -249,6 +249,16 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
         if (halo_bf16 != nullptr && node >= halo_from) continue;
         if (accumulate) continue;   // a later ring phase: the node's rows already hold the earlier phases' sum
         const int nblk = MODE == MODE_DQ ? 1 : 2;
+        if (out_bf16) {
+          uint16_t* ob = reinterpret_cast<uint16_t*>(d_qkv);
+          for (int i = lane; i < F * nblk * (kD / 8); i += 32) {
+            const int r = i / (nblk * (kD / 8)), rem = i - r * (nblk * (kD / 8));
+            const int blk = rem / (kD / 8), c8 = rem - blk * (kD / 8);
+            *reinterpret_cast<uint4*>(ob + ((int64_t)node * F + r) * out_ld + (blk == 0 ? out_c0 : out_c1) + 8 * c8) =
+                make_uint4(0u, 0u, 0u, 0u);
+          }
+          continue;
+        }
         for (int i = lane; i < F * nblk * (kD / 4); i += 32) {
           const int r = i / (nblk * (kD / 4)), rem = i - r * (nblk * (kD / 4));
           const int blk = rem / (kD / 4), c4 = rem - blk * (kD / 4);
@@ -344,6 +354,16 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
         if (halo_bf16 != nullptr && node >= halo_from) continue;
         if (accumulate || grp != 0) continue;   // later ring phase: rows hold the earlier sum; group 0 zero-fills whole rows
         const int nblk = MODE == MODE_DQ ? 1 : 2;
+        if (out_bf16) {
+          uint16_t* ob = reinterpret_cast<uint16_t*>(d_qkv);
+          for (int i = lane; i < F * nblk * (kD / 8); i += 32) {
+            const int r = i / (nblk * (kD / 8)), rem = i - r * (nblk * (kD / 8));
+            const int blk = rem / (kD / 8), c8 = rem - blk * (kD / 8);
+            *reinterpret_cast<uint4*>(ob + ((int64_t)node * F + r) * out_ld + (blk == 0 ? out_c0 : out_c1) + 8 * c8) =
+                make_uint4(0u, 0u, 0u, 0u);
+          }
+          continue;
+        }
         for (int i = lane; i < F * nblk * (kD / 4); i += 32) {
           const int r = i / (nblk * (kD / 4)), rem = i - r * (nblk * (kD / 4));
           const int blk = rem / (kD / 4), c4 = rem - blk * (kD / 4);
@@ -589,7 +609,15 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
             v[x] = (__uint_as_float(a[x]) + lds_f32(racc + (16 * c4 + x) * 512)) * out_scale0;
             sts_f32(racc + (16 * c4 + x) * 512, 0.f);
           }
-          if (row_ok) {
+          if (row_ok && out_bf16) {
+            // gradient rows as bf16 (single-GPU path: the dX projection and the weight-gradient kernel feed bf16 operands)
+            uint16_t* ob = reinterpret_cast<uint16_t*>(d_qkv) + ((int64_t)ns.node * F + row) * out_ld + out_c0 +
+                           (GROUPS == 1 ? 16 * c4 : 32 * ns.grp + 8 * c4);
+#pragma unroll
+            for (int x = 0; x < (GROUPS == 1 ? 16 : 8); x += 8)
+              *reinterpret_cast<uint4*>(ob + x) = make_uint4(pack_bf16x2(v[x], v[x + 1]), pack_bf16x2(v[x + 2], v[x + 3]),
+                                                             pack_bf16x2(v[x + 4], v[x + 5]), pack_bf16x2(v[x + 6], v[x + 7]));
+          } else if (row_ok) {
             // GROUPS == 2 (HD == 16): TMEM columns [16 c4, 16 c4 + 8) are the real columns of padded head c4
             float* oc = GROUPS == 1 ? o + 16 * c4 : o + 32 * ns.grp + 8 * c4;
 #pragma unroll
@@ -800,10 +828,13 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
           const bool is_dv = j4 < 2;
           const float sc = is_dv ? out_scale1 : out_scale0;
           if (GROUPS == 1) {
-            if (halo_bf16 != nullptr && ns.node >= halo_from) {
-              // halo source (multi-GPU): this partial row travels to its owner, written as bf16 [node - halo_from][row][out_ld]
-              uint4* o = reinterpret_cast<uint4*>(halo_bf16 + ((int64_t)(ns.node - halo_from) * F + row) * out_ld +
-                                                  (is_dv ? out_c1 : out_c0) + 32 * (j4 & 1));
+            const bool to_halo = halo_bf16 != nullptr && ns.node >= halo_from;
+            if (to_halo || out_bf16) {
+              // halo source (multi-GPU): this partial row travels to its owner, written as bf16 [node - halo_from][row][out_ld];
+              // out_bf16 (single GPU): every row is written as bf16 for the bf16-fed projection / weight-gradient kernels
+              uint16_t* ob = to_halo ? halo_bf16 + ((int64_t)(ns.node - halo_from) * F + row) * out_ld
+                                     : reinterpret_cast<uint16_t*>(d_qkv) + ((int64_t)ns.node * F + row) * out_ld;
+              uint4* o = reinterpret_cast<uint4*>(ob + (is_dv ? out_c1 : out_c0) + 32 * (j4 & 1));
 #pragma unroll
               for (int x = 0; x < 32; x += 8)
                 o[x >> 3] = make_uint4(pack_bf16x2(__uint_as_float(a[x]) * sc, __uint_as_float(a[x + 1]) * sc),
@@ -826,8 +857,11 @@ attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap own0, const __grid_cons
             for (int u = 0; u < 2; ++u) {
               const int col = (is_dv ? out_c1 : out_c0) + 32 * ns_grp + 8 * (2 * (int)(j4 & 1) + u);
               const uint32_t* au = a + 16 * u;
-              if (halo_bf16 != nullptr && ns.node >= halo_from) {
-                *reinterpret_cast<uint4*>(halo_bf16 + ((int64_t)(ns.node - halo_from) * F + row) * out_ld + col) =
+              const bool to_halo = halo_bf16 != nullptr && ns.node >= halo_from;
+              if (to_halo || out_bf16) {
+                uint16_t* ob = to_halo ? halo_bf16 + ((int64_t)(ns.node - halo_from) * F + row) * out_ld
+                                       : reinterpret_cast<uint16_t*>(d_qkv) + ((int64_t)ns.node * F + row) * out_ld;
+                *reinterpret_cast<uint4*>(ob + col) =
                     make_uint4(pack_bf16x2(__uint_as_float(au[0]) * sc, __uint_as_float(au[1]) * sc),
                                pack_bf16x2(__uint_as_float(au[2]) * sc, __uint_as_float(au[3]) * sc),
                                pack_bf16x2(__uint_as_float(au[4]) * sc, __uint_as_float(au[5]) * sc),
@@ -869,7 +903,7 @@ int launch_bwd(const CUtensorMap& own0, const CUtensorMap& own1, const CUtensorM
                const void* gown0, const void* gown1, const void* goth0, const void* goth1,
                const int32_t* rowptr, const int32_t* nbr, const int32_t* slot_of, const int32_t* lse_map, const int32_t* order,
                const float* lse2, float* delta, float* d_qkv, int* counter, int* status, int N, int F, float s0, float s1, int out_ld, int out_c0,
-               int out_c1, uint16_t* halo_bf16, int halo_from, int accumulate, cudaStream_t stream) {
+               int out_c1, uint16_t* halo_bf16, int halo_from, int accumulate, int out_bf16, cudaStream_t stream) {
   const size_t smem = sizeof(BwdSmem<MODE>) + 1024;
   const int items = N * GROUPS;
   const int grid = items < sm_count() ? items : sm_count();
@@ -880,7 +914,7 @@ int launch_bwd(const CUtensorMap& own0, const CUtensorMap& own1, const CUtensorM
                                           (int)smem));                                                                           \
     attn_bwd_bf16_kernel<HD, MODE, NH_, GROUPS, PROF_><<<grid, threads_of(MODE), smem, stream>>>(                                         \
         own0, own1, oth0, oth1, rowptr, nbr, slot_of, lse_map, order, lse2, delta, d_qkv, counter, status, N, F, s0, s1, out_ld, out_c0,   \
-        out_c1, halo_bf16, halo_from, accumulate, reinterpret_cast<const uint8_t*>(gown0),                                      \
+        out_c1, halo_bf16, halo_from, accumulate, out_bf16, reinterpret_cast<const uint8_t*>(gown0),                                     \
         reinterpret_cast<const uint8_t*>(gown1), reinterpret_cast<const uint8_t*>(goth0),                                       \
         reinterpret_cast<const uint8_t*>(goth1), prof_);                                                                                  \
   } while (0)
@@ -909,7 +943,8 @@ static int bwd_common(int mode, const void* q, const void* k, const void* v, con
                       const int32_t* rowptr, const int32_t* nbr, const int32_t* slot_of, const int32_t* order,
                       const float* lse2, float* delta, float* out, int out_ld, int out_c0, int out_c1, int64_t N_dst, int64_t N_kv, int64_t E, int F, int d,
                       int H, void* workspace, size_t workspace_bytes, void* stream_, void* halo_bf16 = nullptr,
-                      int64_t halo_from = 0, int64_t n_work = -1, int accumulate = 0, const int32_t* lse_map = nullptr) {
+                      int64_t halo_from = 0, int64_t n_work = -1, int accumulate = 0, const int32_t* lse_map = nullptr,
+                      int out_bf16 = 0) {
   AMPCONV_REQUIRE(N_dst >= 0 && N_kv >= 0 && E >= 0 && F > 0 && d > 0 && H > 0 && d % H == 0);
   if (!ampconv_attn_bf16_supported(F, d, H)) return AMPCONV_ERR_UNSUPPORTED;
   const int64_t N_own = mode == MODE_DQ ? N_dst : N_kv;
@@ -935,22 +970,22 @@ static int bwd_common(int mode, const void* q, const void* k, const void* v, con
     // dQ = hd^-1/2 * (dS K)
     if (hd == 8)
       return launch_bwd<16, MODE_DQ, 2>(mq, mg, mk, mv, q, d_agg_bf16, k, v, rowptr, nbr, slot_of, lse_map, order, lse2, delta, out, counter, status, (int)n_work, F,
-                                       inv_sqrt_hd, 0.f, out_ld, out_c0, out_c1, nullptr, 0, accumulate, stream);
+                                       inv_sqrt_hd, 0.f, out_ld, out_c0, out_c1, nullptr, 0, accumulate, out_bf16, stream);
     if (hd == 16)
       return launch_bwd<16, MODE_DQ, 1>(mq, mg, mk, mv, q, d_agg_bf16, k, v, rowptr, nbr, slot_of, lse_map, order, lse2, delta, out, counter, status, (int)n_work, F,
-                                    inv_sqrt_hd, 0.f, out_ld, out_c0, out_c1, nullptr, 0, accumulate, stream);
+                                    inv_sqrt_hd, 0.f, out_ld, out_c0, out_c1, nullptr, 0, accumulate, out_bf16, stream);
     return launch_bwd<32, MODE_DQ, 1>(mq, mg, mk, mv, q, d_agg_bf16, k, v, rowptr, nbr, slot_of, lse_map, order, lse2, delta, out, counter, status, (int)n_work, F,
-                                  inv_sqrt_hd, 0.f, out_ld, out_c0, out_c1, nullptr, 0, accumulate, stream);
+                                  inv_sqrt_hd, 0.f, out_ld, out_c0, out_c1, nullptr, 0, accumulate, out_bf16, stream);
   }
   // dK = hd^-1/2 * dS^T Q = ln2 * dS^T Q'  (Q' = Q * log2e / sqrt(hd)),  dV = P^T dO
   if (hd == 8)
     return launch_bwd<16, MODE_DKV, 2>(mk, mv, mq, mg, k, v, q, d_agg_bf16, rowptr, nbr, slot_of, lse_map, order, lse2, delta, out, counter, status, (int)n_work, F,
-                                      ln2, 1.f, out_ld, out_c0, out_c1, reinterpret_cast<uint16_t*>(halo_bf16), (int)halo_from, 0, stream);
+                                      ln2, 1.f, out_ld, out_c0, out_c1, reinterpret_cast<uint16_t*>(halo_bf16), (int)halo_from, 0, out_bf16, stream);
   if (hd == 16)
     return launch_bwd<16, MODE_DKV, 1>(mk, mv, mq, mg, k, v, q, d_agg_bf16, rowptr, nbr, slot_of, lse_map, order, lse2, delta, out, counter, status, (int)n_work, F,
-                                   ln2, 1.f, out_ld, out_c0, out_c1, reinterpret_cast<uint16_t*>(halo_bf16), (int)halo_from, 0, stream);
+                                   ln2, 1.f, out_ld, out_c0, out_c1, reinterpret_cast<uint16_t*>(halo_bf16), (int)halo_from, 0, out_bf16, stream);
   return launch_bwd<32, MODE_DKV, 1>(mk, mv, mq, mg, k, v, q, d_agg_bf16, rowptr, nbr, slot_of, lse_map, order, lse2, delta, out, counter, status, (int)n_work, F, ln2,
-                                 1.f, out_ld, out_c0, out_c1, reinterpret_cast<uint16_t*>(halo_bf16), (int)halo_from, 0, stream);
+                                 1.f, out_ld, out_c0, out_c1, reinterpret_cast<uint16_t*>(halo_bf16), (int)halo_from, 0, out_bf16, stream);
 }
 
 extern "C" int ampconv_attn_bwd_dq_bf16(const void* q, const void* k, const void* v, const void* d_agg_bf16,
@@ -968,6 +1003,28 @@ extern "C" int ampconv_attn_bwd_dkv_bf16(const void* q, const void* k, const voi
                                          void* workspace, size_t workspace_bytes, void* stream) {
   return bwd_common(MODE_DKV, q, k, v, d_agg_bf16, src_rowptr, src_dst, src_pos, order, lse2, const_cast<float*>(delta), d_qkv,
                     3 * kD, kD, 2 * kD, N, N, E, F, d, H, workspace, workspace_bytes, stream);
+}
+
+// Same two passes with the gradient rows written as bf16 (d_qkv_bf16 [rows, 192]): the consumers -- the dX projection and the
+// in_proj weight-gradient kernel -- feed bf16 operands to the tensor cores anyway, so nothing is lost and 25 GB of HBM traffic
+// per step at the ogbn-arxiv shape are saved (fp32 rows: 16.6 GB written once and read twice).
+extern "C" int ampconv_attn_bwd_dq_bf16_h(const void* q, const void* k, const void* v, const void* d_agg_bf16,
+                                          const float* lse2, const int32_t* dst_rowptr, const int32_t* dst_src,
+                                          const int32_t* order, void* d_qkv_bf16, float* delta, int64_t N, int64_t E, int F,
+                                          int d, int H, void* workspace, size_t workspace_bytes, void* stream) {
+  return bwd_common(MODE_DQ, q, k, v, d_agg_bf16, dst_rowptr, dst_src, nullptr, order, lse2, delta,
+                    reinterpret_cast<float*>(d_qkv_bf16), 3 * kD, 0, 0, N, N, E, F, d, H, workspace, workspace_bytes, stream, nullptr, 0,
+                    -1, 0, nullptr, 1);
+}
+
+extern "C" int ampconv_attn_bwd_dkv_bf16_h(const void* q, const void* k, const void* v, const void* d_agg_bf16,
+                                           const float* lse2, const float* delta, const int32_t* src_rowptr,
+                                           const int32_t* src_dst, const int32_t* src_pos, const int32_t* order,
+                                           void* d_qkv_bf16, int64_t N, int64_t E, int F, int d, int H,
+                                           void* workspace, size_t workspace_bytes, void* stream) {
+  return bwd_common(MODE_DKV, q, k, v, d_agg_bf16, src_rowptr, src_dst, src_pos, order, lse2, const_cast<float*>(delta),
+                    reinterpret_cast<float*>(d_qkv_bf16), 3 * kD, kD, 2 * kD, N, N, E, F, d, H, workspace, workspace_bytes, stream,
+                    nullptr, 0, -1, 0, nullptr, 1);
 }
 
 // Destination-partitioned variants (multi-GPU): q / d_agg cover the num_nodes local destinations, k / v the

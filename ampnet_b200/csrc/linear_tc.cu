@@ -50,7 +50,8 @@ struct LinSmem {
   uint32_t tmem_base;
 };
 
-template <int K, int N, int EPI>
+// IN_BF16: the input rows are bf16 already (the gradient rows of the attention backward): 16-byte chunks are copied as they are.
+template <int K, int N, int EPI, bool IN_BF16 = false>
 __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearArgs args, int* __restrict__ status) {
   using Smem = LinSmem<K, N>;
   extern __shared__ uint8_t smem_raw[];
@@ -95,6 +96,26 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearArgs
       const uint32_t st = it % kStages;
       if (!mbar_wait(&sm.a_empty[st], ((it / kStages) & 1) ^ 1)) { atomicCAS(status, 0, 401 | (blockIdx.x << 16)); break; }
       const int64_t row0 = tile * 128;
+      if constexpr (IN_BF16) {
+        const uint4* xb = reinterpret_cast<const uint4*>(args.x);     // bf16 [rows, K]: K / 8 chunks of 16 bytes per row
+        uint4 v[kChunksPerThread > 8 ? 8 : kChunksPerThread];
+#pragma unroll
+        for (int base = 0; base < kChunksPerThread; base += 8) {
+#pragma unroll
+          for (int u = 0; u < 8 && base + u < kChunksPerThread; ++u) {
+            const int q = (base + u) * kLoadThreads + tid;
+            const int r = q / kChunksPerRow, c = q - r * kChunksPerRow;
+            const int64_t grow = row0 + r;
+            v[u] = grow < args.rows ? __ldg(xb + grow * kChunksPerRow + c) : make_uint4(0u, 0u, 0u, 0u);
+          }
+#pragma unroll
+          for (int u = 0; u < 8 && base + u < kChunksPerThread; ++u) {
+            const int q = (base + u) * kLoadThreads + tid;
+            const int r = q / kChunksPerRow, c = q - r * kChunksPerRow;
+            *reinterpret_cast<uint4*>(sm.a[st][c >> 3] + sw128_offset(r, (c & 7) * 16)) = v[u];
+          }
+        }
+      } else {
       float4 v[kChunksPerThread > 8 ? 8 : kChunksPerThread][2];
 #pragma unroll
       for (int base = 0; base < kChunksPerThread; base += 8) {
@@ -123,6 +144,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearArgs
           pk.w = pack_bf16x2(v[u][1].z, v[u][1].w);
           *reinterpret_cast<uint4*>(sm.a[st][c >> 3] + sw128_offset(r, (c & 7) * 16)) = pk;
         }
+      }
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -219,13 +241,13 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearArgs
   if (warp == kMmaWarp) tmem_dealloc(tmem, kTmemCols);
 }
 
-template <int K, int N, int EPI>
+template <int K, int N, int EPI, bool IN_BF16 = false>
 int launch_linear(const LinearArgs& args, int* status, cudaStream_t stream) {
   const size_t smem = sizeof(LinSmem<K, N>) + 1024;
-  AMPCONV_CUDA_TRY(cudaFuncSetAttribute(linear_tc_kernel<K, N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  AMPCONV_CUDA_TRY(cudaFuncSetAttribute(linear_tc_kernel<K, N, EPI, IN_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t tiles = (args.rows + 127) / 128;
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  linear_tc_kernel<K, N, EPI><<<grid, kThreads, smem, stream>>>(args, status);
+  linear_tc_kernel<K, N, EPI, IN_BF16><<<grid, kThreads, smem, stream>>>(args, status);
   AMPCONV_CHECK_LAUNCH();
   return AMPCONV_OK;
 }
@@ -280,4 +302,16 @@ extern "C" int ampconv_qkv_proj_bwd_input_tc(const float* d_qkv, const float* w,
   LinearArgs a{};
   a.x = d_qkv; a.w = w; a.out0 = d_x; a.rows = rows; a.tokens_per_node = 1; a.q_scale = 1.f;
   return launch_linear<192, 64, EPI_DX>(a, reinterpret_cast<int*>(workspace) + 1, as_stream(stream));
+}
+
+// d_x from bf16 gradient rows d_qkv_bf16 [rows, 192] (ampconv_attn_bwd_*_bf16_h).
+extern "C" int ampconv_qkv_proj_bwd_input_tc_h(const void* d_qkv_bf16, const float* w, float* d_x, int64_t rows, int d,
+                                               void* workspace, void* stream) {
+  AMPCONV_REQUIRE(rows >= 0 && d > 0);
+  if (d != 64) return AMPCONV_ERR_UNSUPPORTED;
+  if (rows == 0) return AMPCONV_OK;
+  AMPCONV_REQUIRE(d_qkv_bf16 && w && d_x && workspace);
+  LinearArgs a{};
+  a.x = reinterpret_cast<const float*>(d_qkv_bf16); a.w = w; a.out0 = d_x; a.rows = rows; a.tokens_per_node = 1; a.q_scale = 1.f;
+  return launch_linear<192, 64, EPI_DX, true>(a, reinterpret_cast<int*>(workspace) + 1, as_stream(stream));
 }

@@ -32,7 +32,8 @@ struct WgSmem {
   uint32_t tmem_base;
 };
 
-template <int MW>
+// A_BF16: the gradient rows A are bf16 already (ampconv_attn_bwd_*_bf16_h): 16-byte chunks are copied as they are.
+template <int MW, bool A_BF16 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ gate,
                 int tokens_per_node, int64_t rows, float* __restrict__ partials, int* __restrict__ status) {
@@ -65,7 +66,27 @@ wgrad_tc_kernel(const float* __restrict__ A, const float* __restrict__ B, const 
       const uint32_t st = it % NS;
       if (!mbar_wait(&sm.empty[st], ((it / NS) & 1) ^ 1)) { atomicCAS(status, 0, 501 | (blockIdx.x << 16)); break; }
       const int64_t row0 = tile * 128;
-      // A tile: 128 rows x MW floats -> NA atoms
+      // A tile: 128 rows x MW values -> NA atoms
+      if constexpr (A_BF16) {
+        const uint4* Ab = reinterpret_cast<const uint4*>(A);
+#pragma unroll
+        for (int base = 0; base < MW / 8; base += 8) {
+          uint4 v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int q = (base + u) * 128 + tid;
+            const int r = q / (MW / 8), c = q - r * (MW / 8);
+            const int64_t grow = row0 + r;
+            v[u] = grow < rows ? __ldg(Ab + grow * (MW / 8) + c) : make_uint4(0u, 0u, 0u, 0u);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int q = (base + u) * 128 + tid;
+            const int r = q / (MW / 8), c = q - r * (MW / 8);
+            *reinterpret_cast<uint4*>(sm.a[st][c >> 3] + sw128_offset(r, (c & 7) * 16)) = v[u];
+          }
+        }
+      } else {
 #pragma unroll
       for (int base = 0; base < MW / 8; base += 8) {
         float4 v[8][2];
@@ -94,6 +115,7 @@ wgrad_tc_kernel(const float* __restrict__ A, const float* __restrict__ B, const 
           pk.w = pack_bf16x2(v[u][1].z, v[u][1].w);
           *reinterpret_cast<uint4*>(sm.a[st][c >> 3] + sw128_offset(r, (c & 7) * 16)) = pk;
         }
+      }
       }
       // B tile: 128 rows x 64 floats
       {
@@ -211,15 +233,15 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partials, int num_
   if (c < 64) d_w[a * 64 + c] = s; else d_b[a] = s;
 }
 
-template <int MW>
+template <int MW, bool A_BF16 = false>
 int launch_wgrad(const float* A, const float* B, const float* gate, int tokens_per_node, int64_t rows,
                  float* d_w, float* d_b, float* partials, size_t partial_bytes, int* status, cudaStream_t stream) {
   const int64_t tiles = (rows + 127) / 128;
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   if ((size_t)grid * MW * 65 * sizeof(float) > partial_bytes) return AMPCONV_ERR_WORKSPACE;
   const size_t smem = sizeof(WgSmem<MW>) + 1024;
-  AMPCONV_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel<MW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  wgrad_tc_kernel<MW><<<grid, kThreads, smem, stream>>>(A, B, gate, tokens_per_node, rows, partials, status);
+  AMPCONV_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel<MW, A_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  wgrad_tc_kernel<MW, A_BF16><<<grid, kThreads, smem, stream>>>(A, B, gate, tokens_per_node, rows, partials, status);
   AMPCONV_CHECK_LAUNCH();
   wgrad_reduce_kernel<<<(MW * 65 + 255) / 256, 256, 0, stream>>>(partials, grid, MW, d_w, d_b);
   AMPCONV_CHECK_LAUNCH();
@@ -262,4 +284,21 @@ extern "C" int ampconv_qkv_proj_bwd_params_tc(const float* x, const float* d_qkv
   AMPCONV_REQUIRE(x && d_qkv && ws && workspace);
   return launch_wgrad<192>(d_qkv, x, nullptr, 1, rows, d_w, d_b, reinterpret_cast<float*>(ws), ws_bytes,
                            reinterpret_cast<int*>(workspace) + 1, stream);
+}
+
+// in_proj parameter gradients from bf16 gradient rows d_qkv_bf16 [rows, 192] (ampconv_attn_bwd_*_bf16_h).
+extern "C" int ampconv_qkv_proj_bwd_params_tc_h(const float* x, const void* d_qkv_bf16, float* d_w, float* d_b,
+                                                int64_t rows, int d, void* ws, size_t ws_bytes, void* workspace,
+                                                void* stream_) {
+  AMPCONV_REQUIRE(rows >= 0 && d_w && d_b);
+  if (d != 64) return AMPCONV_ERR_UNSUPPORTED;
+  cudaStream_t stream = as_stream(stream_);
+  if (rows == 0) {
+    AMPCONV_CUDA_TRY(cudaMemsetAsync(d_w, 0, sizeof(float) * 3 * d * d, stream));
+    AMPCONV_CUDA_TRY(cudaMemsetAsync(d_b, 0, sizeof(float) * 3 * d, stream));
+    return AMPCONV_OK;
+  }
+  AMPCONV_REQUIRE(x && d_qkv_bf16 && ws && workspace);
+  return launch_wgrad<192, true>(reinterpret_cast<const float*>(d_qkv_bf16), x, nullptr, 1, rows, d_w, d_b,
+                                 reinterpret_cast<float*>(ws), ws_bytes, reinterpret_cast<int*>(workspace) + 1, stream);
 }

@@ -221,17 +221,18 @@ def _backward_bf16(saved, x, w_in, w_out, d_out):
               _lib.i64(n), _lib.i32(f), _lib.i32(d), bws, st)
     _lib.call("ampconv_out_proj_bwd_params_tc", d_out, saved.agg, g.has_in, d_w_out, d_b_out,
               _lib.i64(n), _lib.i32(f), _lib.i32(d), ws, _lib.size_t(ws.numel()), bws, st)
-    d_qkv = torch.empty((rows, 3 * d), dtype=torch.float32, device=dev)
+    # gradient rows dQ | dK | dV as bf16: their consumers feed bf16 operands to the tensor cores anyway
+    d_qkv = torch.empty((rows, 3 * d), dtype=torch.bfloat16, device=dev)
     delta = torch.empty_like(lse2)
     tail = (_lib.i64(n), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(h), bws, _lib.size_t(bws.numel() * 4), st)
-    _lib.call("ampconv_attn_bwd_dq_bf16", q, k, v, d_agg, lse2, g.dst_rowptr, g.dst_src, g.order_dst, d_qkv, delta, *tail)
-    _lib.call("ampconv_attn_bwd_dkv_bf16", q, k, v, d_agg, lse2, delta, g.src_rowptr, g.src_dst, g.src_pos,
+    _lib.call("ampconv_attn_bwd_dq_bf16_h", q, k, v, d_agg, lse2, g.dst_rowptr, g.dst_src, g.order_dst, d_qkv, delta, *tail)
+    _lib.call("ampconv_attn_bwd_dkv_bf16_h", q, k, v, d_agg, lse2, delta, g.src_rowptr, g.src_dst, g.src_pos,
               g.order_src, d_qkv, *tail)
     d_x = torch.empty_like(x)
     d_w_in = torch.empty_like(w_in)
     d_b_in = torch.empty(3 * d, dtype=torch.float32, device=dev)
-    _lib.call("ampconv_qkv_proj_bwd_input_tc", d_qkv, w_in, d_x, _lib.i64(rows), _lib.i32(d), bws, st)
-    _lib.call("ampconv_qkv_proj_bwd_params_tc", x, d_qkv, d_w_in, d_b_in,
+    _lib.call("ampconv_qkv_proj_bwd_input_tc_h", d_qkv, w_in, d_x, _lib.i64(rows), _lib.i32(d), bws, st)
+    _lib.call("ampconv_qkv_proj_bwd_params_tc_h", x, d_qkv, d_w_in, d_b_in,
               _lib.i64(rows), _lib.i32(d), ws, _lib.size_t(ws.numel()), bws, st)
     _post_status(bws, "AMPConv backward (bf16)")
     return d_x, d_w_in, d_b_in, d_w_out, d_b_out
@@ -507,10 +508,11 @@ def profile_stages(x, graph, w_in, b_in, w_out, b_out, num_heads, d_out, mode, r
             delta2 = torch.empty_like(lse2)
             tail = (_lib.i64(n), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(num_heads), bws,
                     _lib.size_t(bws.numel() * 4), st)
-            calls["attn_bwd_dq"] = lambda: _lib.call("ampconv_attn_bwd_dq_bf16", q, k, v, d_agg16, lse2,
-                                                     graph.dst_rowptr, graph.dst_src, graph.order_dst, d_qkv, delta2, *tail)
-            calls["attn_bwd_dkv"] = lambda: _lib.call("ampconv_attn_bwd_dkv_bf16", q, k, v, d_agg16, lse2, delta2,
-                                                      graph.src_rowptr, graph.src_dst, graph.src_pos, graph.order_src, d_qkv, *tail)
+            d_qkv16 = torch.empty((rows, 3 * d), dtype=torch.bfloat16, device=dev)     # the product path's bf16 gradient rows
+            calls["attn_bwd_dq"] = lambda: _lib.call("ampconv_attn_bwd_dq_bf16_h", q, k, v, d_agg16, lse2,
+                                                     graph.dst_rowptr, graph.dst_src, graph.order_dst, d_qkv16, delta2, *tail)
+            calls["attn_bwd_dkv"] = lambda: _lib.call("ampconv_attn_bwd_dkv_bf16_h", q, k, v, d_agg16, lse2, delta2,
+                                                      graph.src_rowptr, graph.src_dst, graph.src_pos, graph.order_src, d_qkv16, *tail)
         else:
             delta = torch.empty_like(saved.lse)
             calls["attn_bwd_dq"] = lambda: _lib.call("ampconv_attn_bwd_dq_f32", saved.qkv, d_agg, saved.lse,

@@ -256,6 +256,25 @@ AMPCONV_API int ampconv_qkv_proj_bwd_params_tc(const float* x, const float* d_qk
                                    int64_t rows, int d, void* scratch, size_t scratch_bytes, void* workspace,
                                    void* stream);
 
+/* The backward with bf16 gradient rows (the single-GPU product path): _dq_h / _dkv_h write d_qkv_bf16 [rows, 3d] bf16 instead
+ * of fp32, _bwd_input_tc_h / _bwd_params_tc_h consume it.  The projection and weight-gradient kernels feed bf16 operands to
+ * the tensor cores in either case, so the results are those of the fp32-row entry points; the rows cost a third of the HBM
+ * traffic (written once, read twice). */
+AMPCONV_API int ampconv_attn_bwd_dq_bf16_h(const void* q, const void* k, const void* v, const void* d_agg_bf16,
+                               const float* lse2, const int32_t* dst_rowptr, const int32_t* dst_src,
+                               const int32_t* order, void* d_qkv_bf16, float* delta, int64_t num_nodes, int64_t num_edges,
+                               int F, int d, int H, void* workspace, size_t workspace_bytes, void* stream);
+AMPCONV_API int ampconv_attn_bwd_dkv_bf16_h(const void* q, const void* k, const void* v, const void* d_agg_bf16,
+                                const float* lse2, const float* delta, const int32_t* src_rowptr,
+                                const int32_t* src_dst, const int32_t* src_pos, const int32_t* order, void* d_qkv_bf16,
+                                int64_t num_nodes, int64_t num_edges, int F, int d, int H,
+                                void* workspace, size_t workspace_bytes, void* stream);
+AMPCONV_API int ampconv_qkv_proj_bwd_input_tc_h(const void* d_qkv_bf16, const float* in_proj_weight, float* d_x,
+                                    int64_t rows, int d, void* workspace, void* stream);
+AMPCONV_API int ampconv_qkv_proj_bwd_params_tc_h(const float* x, const void* d_qkv_bf16, float* d_w, float* d_b,
+                                     int64_t rows, int d, void* scratch, size_t scratch_bytes, void* workspace,
+                                     void* stream);
+
 /* Destination-partitioned variants of the three attention kernels (multi-GPU): q / d_agg cover the
  * num_nodes LOCAL destinations, k / v the num_kv_nodes rows of the all-gathered K / V; graph views come from
  * ampconv_graph_build_bipartite.  _dq writes d_q fp32 [num_nodes*F, d]; _dkv writes the partial d_k | d_v
