@@ -904,12 +904,6 @@ def dist_amp_conv(x_local, pg, w_in, b_in, w_out, b_out, num_heads, group=None, 
 
     if key is None:
         key = ("param", w_in.data_ptr())
-    if F_.bf16_supported(f, d, num_heads) and not F_.bf16_grouped_supported(f, d, num_heads):
+    if F_.bf16_supported(f, d, num_heads):
         return layer(x_local, w_in, b_in, w_out, b_out, num_heads, key)
-    if F_.bf16_grouped_supported(f, d, num_heads):
-        # head_dim 8 without the native kernels: two 4-head passes over zero-padded heads, composed by autograd
-        # (functional.hd8_compose); every pass is a full partitioned layer with its own engine
-        calls = iter(range(2))
-        return F_.hd8_compose(lambda x_, wi, bi, wo, bo, heads: layer(x_, wi, bi, wo, bo, heads, (key, "group", next(calls))),
-                              x_local, w_in, b_in, w_out, b_out)
     raise ValueError("the partitioned path uses the tcgen05 family: embed_dim 64, head_dim 8, 16 or 32, F <= 128")

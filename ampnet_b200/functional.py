@@ -21,27 +21,13 @@ def bf16_supported(f, d, h):
     return bool(lib.ampconv_attn_bf16_supported(int(f), int(d), int(h)))
 
 
-import os
-
-# head_dim 8 (embed 64, 8 heads: the ogbn-products shape) is native to the tcgen05 kernels (zero-padding TMA boxes, one launch
-# per pass).  AMPNET_B200_HD8=grouped selects the round-1 head-group decomposition instead (two launches over padded copies;
-# kept for A/B timing only).
-HD8_GROUPED = os.environ.get("AMPNET_B200_HD8", "") == "grouped"
-
-
-def bf16_grouped_supported(f, d, h):
-    """embed 64 with 8 heads of 8 through the head-group decomposition (two groups of four zero-padded heads)."""
-    return HD8_GROUPED and d == 64 and h == 8 and bf16_supported(f, 64, 4)
-
-
 def resolve_mode(mode, f, d, h):
-    """-> "fp32" | "bf16" | "bf16g" (the tensor-core family through the head-group decomposition)."""
+    """-> "fp32" | "bf16".  The tcgen05 family covers embed 64 with head_dim 32, 16 and 8 (the latter -- the ogbn-products shape --
+    as work items (node, head group) whose tiles are zero-padded to 16 columns per head on the way into shared memory)."""
     if mode not in MODES:
         raise ValueError(f"unknown mode {mode!r}; available: {MODES}")
     if mode == "fp32":
         return mode
-    if bf16_grouped_supported(f, d, h):
-        return "bf16g"
     if bf16_supported(f, d, h):
         return "bf16"
     if mode == "bf16":
@@ -103,12 +89,11 @@ def _param_grad_ws(out_dim, in_dim, dev):
 class _Saved:
     """What the last forward of a layer keeps for backward and for the lazy side outputs."""
 
-    def __init__(self, mode, graph, shape, qkv, agg, lse, bf16=None, inputs=None, groups=None):
+    def __init__(self, mode, graph, shape, qkv, agg, lse, bf16=None, inputs=None):
         self.mode, self.graph, self.shape = mode, graph, shape
         self.qkv, self.agg, self.lse = qkv, agg, lse
         self.bf16 = bf16          # (q, k, v, lse2, workspace) of the tensor-core family
         self.inputs = inputs      # (x, w_in, b_in): lets the fp32 views be rebuilt lazily
-        self.groups = groups      # "bf16g": one (q, k, v, lse2) per head group
 
     def ensure_fp32_views(self):
         """fp32 qkv and natural-log lse (needed by the fp32 kernels) for a forward that ran in bf16 mode."""
@@ -119,9 +104,7 @@ class _Saved:
             self.qkv = torch.empty((n * f, 3 * d), dtype=torch.float32, device=dev)
             with torch.cuda.device(dev):
                 _lib.call("ampconv_qkv_proj_f32", x, w_in, b_in, self.qkv, _lib.i64(n * f), _lib.i32(d), _stream(dev))
-            # head-group decomposition: group g holds heads 4g .. 4g+3, so concatenating along the head axis restores the order
-            lse2 = self.bf16[3] if self.groups is None else torch.cat([g[3] for g in self.groups], dim=1)
-            self.lse = (lse2[:, :, :f] * LN2).contiguous()
+            self.lse = (self.bf16[3][:, :, :f] * LN2).contiguous()
         return self
 
 
@@ -238,126 +221,6 @@ def _backward_bf16(saved, x, w_in, w_out, d_out):
     return d_x, d_w_in, d_b_in, d_w_out, d_b_out
 
 
-# ---------------------------------------------------------------------------------------------------------------------
-# head_dim 8 (embed 64, 8 heads: SURVEY.md config C5) on the head_dim-16 tensor-core kernels.
-#
-# Heads 4g .. 4g+3 (g = 0, 1) occupy the contiguous columns [32g, 32g+32) of every projected token.  A group is run as an
-# embed-64 / 4-head problem whose heads are 8 real + 8 ZERO columns: padded column 16*hh + t (t < 8) <- true column
-# 32g + 8*hh + t.  Zero columns change neither Q_h K_h^T nor P_h V_h, so each group's launch computes exactly its four
-# heads' attention (the softmax scale 1/sqrt(8) travels in the Q' pre-scaling; the dQ kernel applies 1/sqrt(16) itself,
-# which the compaction below corrects by sqrt(2)).  The padded operands come out of the unchanged node-level projection
-# kernels fed with zero-padded weight rows / columns; the results are compacted back with plain tensor indexing.  Work per
-# edge = 2 launches x 4 heads x F^2 exponentials = the 8 F^2 the shape needs on the binding pipe; the tensor pipe and the
-# gather do twice the useful work, neither is close to its limit.
-# ---------------------------------------------------------------------------------------------------------------------
-def _pad_head_rows(w, g):
-    """w [64, ...] (rows = projected columns) -> [64, ...]: rows 16*hh + t (t < 8) = w[32g + 8*hh + t], the rest zero."""
-    out = w.new_zeros((4, 16) + tuple(w.shape[1:]))
-    out[:, :8] = w[32 * g:32 * g + 32].reshape((4, 8) + tuple(w.shape[1:]))
-    return out.reshape((64,) + tuple(w.shape[1:]))
-
-
-def hd8_group_params(w_in, b_in, w_out, g):
-    """Zero-padded parameters of head group g: in_proj [192, 64] / [192] (q | k | v sections) and out_proj columns [64, 64]."""
-    w_in_g = torch.cat([_pad_head_rows(w_in[64 * s:64 * s + 64], g) for s in range(3)], dim=0).contiguous()
-    b_in_g = torch.cat([_pad_head_rows(b_in[64 * s:64 * s + 64], g) for s in range(3)], dim=0).contiguous()
-    w_out_g = _pad_head_rows(w_out.t(), g).t().contiguous()
-    return w_in_g, b_in_g, w_out_g
-
-
-def hd8_compact(per_group, sections):
-    """per_group[g]: [rows, sections*64] in the padded layout -> [rows, sections*64] in the true layout
-    (column s*64 + 32g + 8*hh + t <- group g, column s*64 + 16*hh + t)."""
-    rows = per_group[0].shape[0]
-    parts = [t.view(rows, sections, 4, 16)[..., :8] for t in per_group]
-    return torch.stack(parts, dim=2).reshape(rows, sections * 64)
-
-
-def hd8_compose(layer_fn, x, w_in, b_in, w_out, b_out):
-    """The same decomposition at the autograd level: ``layer_fn(x, w_in, b_in, w_out, b_out, num_heads)`` is any differentiable
-    embed-64 AMPConv layer; the 8-head layer is the sum of two 4-head calls with zero-padded parameters (built with
-    differentiable tensor ops, so un-padding the parameter gradients is autograd's job).  The inner layer scales its
-    scores by 1/sqrt(16): the padded query rows carry the missing sqrt(2); out_proj's bias goes to the first call only.
-    Used where the layer body is not the single-GPU one (``distributed.dist_amp_conv``); costs the node-level kernels twice."""
-    out = None
-    q_scale = torch.cat([w_in.new_full((64,), 2.0 ** 0.5), w_in.new_ones(128)])
-    for g in range(2):
-        w_in_g, b_in_g, w_out_g = hd8_group_params(w_in, b_in, w_out, g)
-        o = layer_fn(x, w_in_g * q_scale[:, None], b_in_g * q_scale, w_out_g, b_out if g == 0 else torch.zeros_like(b_out), 4)
-        out = o if out is None else out + o
-    return out
-
-
-def _forward_bf16_hd8(x, graph, w_in, b_in, w_out, b_out, num_heads):
-    n, width = x.shape
-    d = w_in.shape[1]
-    f = width // d
-    dev = x.device
-    e = graph.num_edges
-    st = _stream(dev)
-    rows = n * f
-    out = torch.empty((n, width), dtype=torch.float32, device=dev)
-    ws = torch.zeros(64, dtype=torch.int32, device=dev)
-    groups, aggs = [], []
-    for g in range(2):
-        w_in_g, b_in_g, _ = hd8_group_params(w_in.detach(), b_in.detach(), w_out.detach(), g)
-        q = torch.empty((rows, d), dtype=torch.bfloat16, device=dev)
-        k = torch.empty_like(q)
-        v = torch.empty_like(q)
-        agg_g = torch.empty((rows, d), dtype=torch.float32, device=dev)
-        lse2 = torch.empty((e, 4, (f + 3) // 4 * 4), dtype=torch.float32, device=dev)
-        _lib.call("ampconv_qkv_proj_tc", x, w_in_g, b_in_g, q, k, v, _lib.i64(rows), _lib.i32(d),
-                  _lib.f32(LOG2E / 8 ** 0.5), ws, st)
-        _lib.call("ampconv_attn_fwd_bf16", q, k, v, graph.dst_rowptr, graph.dst_src, graph.inv_deg, graph.order_dst, agg_g, lse2,
-                  _lib.i64(n), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(4),
-                  ws, _lib.size_t(ws.numel() * 4), st)
-        groups.append((q, k, v, lse2))
-        aggs.append(agg_g)
-    agg = hd8_compact(aggs, 1)
-    _lib.call("ampconv_out_proj_tc", agg, w_out, b_out, graph.has_in, out,
-              _lib.i64(n), _lib.i32(f), _lib.i32(d), ws, st)
-    saved = _Saved("bf16g", graph, (n, e, f, d, num_heads), None, agg, None, bf16=(None, None, None, None, ws),
-                   inputs=(x, w_in.detach(), b_in.detach()), groups=groups)
-    return out, saved
-
-
-def _backward_bf16_hd8(saved, x, w_in, w_out, d_out):
-    n, e, f, d, h = saved.shape
-    g_ = saved.graph
-    dev = x.device
-    st = _stream(dev)
-    rows = n * f
-    bws = saved.bf16[4]
-    d_out = d_out.contiguous()
-    d_w_out = torch.empty_like(w_out)
-    d_b_out = torch.empty(d, dtype=torch.float32, device=dev)
-    ws = _param_grad_ws(3 * d, d, dev)
-    _lib.call("ampconv_out_proj_bwd_params_tc", d_out, saved.agg, g_.has_in, d_w_out, d_b_out,
-              _lib.i64(n), _lib.i32(f), _lib.i32(d), ws, _lib.size_t(ws.numel()), bws, st)
-    tail = (_lib.i64(n), _lib.i64(e), _lib.i32(f), _lib.i32(d), _lib.i32(4), bws, _lib.size_t(bws.numel() * 4), st)
-    d_qkv_groups = []
-    for g, (q, k, v, lse2) in enumerate(saved.groups):
-        _, _, w_out_g = hd8_group_params(w_in, w_in.new_zeros(3 * d), w_out, g)
-        d_agg = torch.empty((rows, d), dtype=torch.bfloat16, device=dev)
-        _lib.call("ampconv_out_proj_bwd_input_tc", d_out, w_out_g, g_.inv_deg, d_agg,
-                  _lib.i64(n), _lib.i32(f), _lib.i32(d), bws, st)
-        d_qkv_g = torch.empty((rows, 3 * d), dtype=torch.float32, device=dev)
-        delta = torch.empty_like(lse2)
-        _lib.call("ampconv_attn_bwd_dq_bf16", q, k, v, d_agg, lse2, g_.dst_rowptr, g_.dst_src, g_.order_dst, d_qkv_g, delta, *tail)
-        _lib.call("ampconv_attn_bwd_dkv_bf16", q, k, v, d_agg, lse2, delta, g_.src_rowptr, g_.src_dst, g_.src_pos,
-                  g_.order_src, d_qkv_g, *tail)
-        d_qkv_groups.append(d_qkv_g)
-    d_qkv = hd8_compact(d_qkv_groups, 3)
-    d_qkv[:, :d] *= 2.0 ** 0.5          # the dQ kernel scaled by 1/sqrt(16); the layer's head_dim is 8
-    d_x = torch.empty_like(x)
-    d_w_in = torch.empty_like(w_in)
-    d_b_in = torch.empty(3 * d, dtype=torch.float32, device=dev)
-    _lib.call("ampconv_qkv_proj_bwd_input_tc", d_qkv, w_in, d_x, _lib.i64(rows), _lib.i32(d), bws, st)
-    _lib.call("ampconv_qkv_proj_bwd_params_tc", x, d_qkv, d_w_in, d_b_in,
-              _lib.i64(rows), _lib.i32(d), ws, _lib.size_t(ws.numel()), bws, st)
-    return d_x, d_w_in, d_b_in, d_w_out, d_b_out
-
-
 BF16_BACKWARD = "tcgen05"   # "fp32" routes the backward of a bf16-mode forward through the fp32 kernels (debug aid)
 
 
@@ -365,7 +228,7 @@ class _AMPConvFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w_in, b_in, w_out, b_out, graph, num_heads, mode, holder):
         with torch.cuda.device(x.device):
-            fwd = {"bf16": _forward_bf16, "bf16g": _forward_bf16_hd8}.get(mode, _forward_fp32)
+            fwd = _forward_bf16 if mode == "bf16" else _forward_fp32
             out, saved = fwd(x, graph, w_in, b_in, w_out, b_out, num_heads)
         ctx.save_for_backward(x, w_in, w_out)
         ctx.saved_state = saved
@@ -380,7 +243,7 @@ class _AMPConvFunction(torch.autograd.Function):
         with torch.cuda.device(x.device):
             bwd = _backward_fp32
             if BF16_BACKWARD == "tcgen05":
-                bwd = {"bf16": _backward_bf16, "bf16g": _backward_bf16_hd8}.get(ctx.saved_state.mode, _backward_fp32)
+                bwd = _backward_bf16 if ctx.saved_state.mode == "bf16" else _backward_fp32
             d_x, d_w_in, d_b_in, d_w_out, d_b_out = bwd(ctx.saved_state, x, w_in, w_out, d_out)
         return d_x, d_w_in, d_b_in, d_w_out, d_b_out, None, None, None, None
 

@@ -408,26 +408,32 @@ def run_ours(args):
     feed.release()
 
     # ---- per-kernel durations of the attention kernels (CUDA events on the launching stream)
-    if F_.resolve_mode(args.mode, f, d, h) == "bf16g":
-        # head-group decomposition (two launches per pass): per-kernel roofline not itemised
-        kern_ms = {"attn_fwd": float("nan"), "attn_bwd_dq": float("nan"), "attn_bwd_dkv": ms_step}
-    else:
-        kern_ms = profile_attention_kernels(conv, x_dev, edge_index, d_out, args.mode, reps=max(2, min(args.steps, 5)))
+    kern_ms = profile_attention_kernels(conv, x_dev, edge_index, d_out, args.mode, reps=max(2, min(args.steps, 5)))
     alg = algorithmic_bytes(spec, args.mode)
     pk = peaks()
-    dominant = max(kern_ms, key=lambda k_: kern_ms[k_] if kern_ms[k_] == kern_ms[k_] else -1.0)
+    dominant = max(kern_ms, key=kern_ms.get)
     achieved = alg[dominant] / (kern_ms[dominant] * 1e-3) / 1e9
     traffic, traffic_src = ncu_traffic(args.workload, dominant)
     # the unit that actually binds these kernels is MUFU (exp2): H*F^2 exponentials per edge and pass at 16 / clk / SM
     exps = float(e) * h * f * f
     sm_clk = 148 * 1.965e9
     mufu = {k: exps / (v * 1e-3) / sm_clk / 16.0 for k, v in kern_ms.items()}
+    # the three bounds of SURVEY 8(d) side by side: HBM (the dominant kernel, `frac`), tensor (whole step, algorithmic FLOPs
+    # 14 F^2 d E + 24 F d^2 N against the sustained bf16 peak) and MUFU exp2 (per kernel)
+    flops = 14.0 * f * f * d * e + 24.0 * f * d * d * n
+    tflops = flops / (ms_step * 1e-3) / 1e12
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": pk["source"], "kernel_ms": kern_ms, "algorithmic_bytes": alg,
+                "hbm_frac_per_kernel": {k: alg[k] / (v * 1e-3) / 1e9 / pk["hbm_gbs"] for k, v in kern_ms.items()},
+                "tensor": {"achieved_tflops": tflops, "peak_tflops": pk["bf16_tflops"], "frac": tflops / pk["bf16_tflops"],
+                           "scope": "whole step, algorithmic FLOPs (zero-padding of head_dim 8 and F < 128 not counted)"},
+                "binding": "none of the three pipes saturates: these kernels are bound by the latency between their pipeline stages "
+                           "(ncu: XU 52-63 %, issue slots 50-64 %, tensor 8-27 %, DRAM 20-24 %; profiles/r02_ncu_attn_c4s_full.txt)",
                 "mufu_frac": {"note": "exponentials per second relative to the MUFU exp2 issue peak (16 per clk per SM at 1.965 GHz, "
-                                      "148 SMs), the binding pipe of all three kernels at head_dim 16; the forward evaluates "
-                                      "a quarter of its exponentials on the FMA pipe instead", **mufu}}
+                                      "148 SMs: tools/mufu_probe.cu measures 15.98 per clk per SM), the busiest pipe of all three kernels; "
+                                      "the forward and the dK/dV pass evaluate a quarter of their exponentials on the FMA pipe instead",
+                              **mufu}}
 
     if rank != 0:
         return

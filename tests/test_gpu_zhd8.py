@@ -1,6 +1,6 @@
 """head_dim 8 (embed 64, 8 heads: SURVEY.md config C5, the ogbn-products token shape) on the tensor-core family: one launch
-per pass, work items = (node, head group), tiles zero-padded to 16 columns per head by the TMA box itself (csrc/umma.cuh:
-make_tensor_map_bf16_hd8).  Same 2e-2 bar as every other bf16-mode shape."""
+per pass, work items = (node, head group), tiles zero-padded to 16 columns per head on the way into shared memory (cp.async
+into the swizzled head_dim-16 layout, csrc/umma.cuh: load_padded_tile).  Same 2e-2 bar as every other bf16-mode shape."""
 import numpy as np
 import pytest
 import torch
